@@ -1,0 +1,25 @@
+"""B200-native (sm_100a) multi-scale deformable attention forward for Co-DETR.
+
+Import name: ``codetr_b200`` (the directory keeps the repo-mandated name
+``co-detr-tensorrt_b200``, which is not a Python identifier; ``codetr_b200.py`` at the repo
+root loads it under the importable name).
+
+Importing the package loads ``csrc/libmsda_b200.so`` and registers
+``torch.ops.codetr.multi_scale_deformable_attention`` with the reference's schema.  It raises if
+the library has not been built: there is no CPU or PyTorch fallback.
+"""
+from . import _native
+from ._native import (FLAG_FORCE_GENERIC, FLAG_LINEAR_ORDER, FLAG_MATH_EXACT, FLAG_MATH_FHFMA, FLAG_NO_STAGING,
+                      NativeLibraryError, build_native, last_variant, launch_count)
+from . import workloads
+from . import sharding
+from . import ops
+from .ops import (HostForward, forward_fused, forward_into, multi_scale_deformable_attention, plugin_enqueue,
+                  set_default_flags)
+
+__all__ = [
+    "multi_scale_deformable_attention", "forward_into", "forward_fused", "plugin_enqueue", "HostForward",
+    "set_default_flags", "build_native", "launch_count", "last_variant", "workloads", "sharding",
+    "FLAG_FORCE_GENERIC", "FLAG_LINEAR_ORDER", "FLAG_MATH_EXACT", "FLAG_MATH_FHFMA", "FLAG_NO_STAGING",
+    "NativeLibraryError",
+]

@@ -1,0 +1,151 @@
+"""Loader (and in-tree builder) of the C-ABI library ``libmsda_b200.so``.
+
+The library is compiled from ``csrc/msda_sm100.cu`` for ``sm_100a`` only and is
+the *only* compute path of this package: if it cannot be loaded the package
+raises -- there is deliberately no PyTorch/CPU fallback (the reference's module
+falls back to ``multi_scale_deformable_attention_pytorch`` for CPU tensors,
+/root/reference/codetr/multi_scale_deformable_attention.py:207-210; here that
+function exists only as test infrastructure under ``oracle/``).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import shutil
+import subprocess
+from typing import List, Optional
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+_REPO_ROOT = os.path.dirname(_PKG_DIR)
+CSRC_DIR = os.path.join(_PKG_DIR, "csrc")
+INCLUDE_DIR = os.path.join(_REPO_ROOT, "include")
+LIB_PATH = os.path.join(CSRC_DIR, "libmsda_b200.so")
+SOURCES = [os.path.join(CSRC_DIR, "msda_sm100.cu")]
+HEADERS = [os.path.join(INCLUDE_DIR, "msda_b200.h")]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-shared",
+    "-diag-suppress", "177",
+]
+
+# every symbol include/msda_b200.h declares
+EXPORTED_SYMBOLS = [
+    "msda_b200_forward",
+    "msda_b200_plugin_enqueue",
+    "msda_b200_forward_fused",
+    "msda_b200_host_workspace_bytes",
+    "msda_b200_forward_host",
+    "msda_b200_abi_version",
+    "msda_b200_error_string",
+    "msda_b200_launch_count",
+    "msda_b200_last_variant",
+    "msda_b200_algorithmic_hbm_bytes",
+    "msda_b200_algorithmic_gather_bytes",
+    "msda_b200_read_probe",
+]
+
+DTYPE_F32, DTYPE_F16, DTYPE_BF16, DTYPE_F64 = 0, 1, 2, 3
+FLAG_FORCE_GENERIC = 1 << 0
+FLAG_LINEAR_ORDER = 1 << 1
+FLAG_MATH_FHFMA = 1 << 2
+FLAG_MATH_EXACT = 1 << 3
+FLAG_NO_STAGING = 1 << 4
+
+
+class NativeLibraryError(RuntimeError):
+    pass
+
+
+def _nvcc() -> str:
+    cand = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "bin", "nvcc")
+    if os.path.isfile(cand):
+        return cand
+    found = shutil.which("nvcc")
+    if not found:
+        raise NativeLibraryError("nvcc not found; cannot build libmsda_b200.so")
+    return found
+
+
+def is_stale() -> bool:
+    if not os.path.isfile(LIB_PATH):
+        return True
+    built = os.path.getmtime(LIB_PATH)
+    return any(os.path.getmtime(f) > built for f in SOURCES + HEADERS)
+
+
+def build_native(force: bool = False, verbose: bool = False, extra_flags: Optional[List[str]] = None) -> str:
+    """Compile the CUDA sources in-tree for sm_100a (cross-compiles without a GPU)."""
+    if not force and not is_stale():
+        return LIB_PATH
+    cmd = [_nvcc(), *NVCC_FLAGS, *(extra_flags or []), "-I", INCLUDE_DIR, "-o", LIB_PATH, *SOURCES]
+    if verbose:
+        cmd.insert(1, "-Xptxas")
+        cmd.insert(2, "-v")
+    env = dict(os.environ)
+    # the image exports CC/CXX wrappers that nvcc does not need; use the system host compiler
+    proc = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    if proc.returncode != 0:
+        raise NativeLibraryError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+    if verbose:
+        print(proc.stderr)
+    return LIB_PATH
+
+
+_lib: Optional[ctypes.CDLL] = None
+
+
+def load() -> ctypes.CDLL:
+    """dlopen the library and declare the prototypes of include/msda_b200.h."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise NativeLibraryError(
+            f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or codetr_b200.build_native()).  There is no CPU fallback."
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    missing = [s for s in EXPORTED_SYMBOLS if not hasattr(lib, s)]
+    if missing:
+        raise NativeLibraryError(f"{LIB_PATH} lacks symbols {missing}; rebuild it")
+    vp, i64, ci, cu = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_uint
+    lib.msda_b200_forward.restype = ci
+    lib.msda_b200_forward.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, i64, i64, i64, ci, cu, vp]
+    lib.msda_b200_forward_fused.restype = ci
+    lib.msda_b200_forward_fused.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, i64, i64, i64, ci, cu, vp]
+    lib.msda_b200_plugin_enqueue.restype = ci
+    lib.msda_b200_plugin_enqueue.argtypes = [vp, vp, ci, vp, vp, vp, i64, vp]
+    lib.msda_b200_host_workspace_bytes.restype = ctypes.c_size_t
+    lib.msda_b200_host_workspace_bytes.argtypes = [i64, i64, i64, i64, i64, i64, i64, ci]
+    lib.msda_b200_forward_host.restype = ci
+    lib.msda_b200_forward_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, ctypes.c_size_t,
+                                           i64, i64, i64, i64, i64, i64, i64, i64, ci, cu, vp]
+    lib.msda_b200_abi_version.restype = ci
+    lib.msda_b200_error_string.restype = ctypes.c_char_p
+    lib.msda_b200_error_string.argtypes = [ci]
+    lib.msda_b200_launch_count.restype = ctypes.c_uint64
+    lib.msda_b200_last_variant.restype = ctypes.c_char_p
+    lib.msda_b200_algorithmic_hbm_bytes.restype = ctypes.c_uint64
+    lib.msda_b200_algorithmic_hbm_bytes.argtypes = [i64, i64, i64, i64, i64, i64, i64, ci]
+    lib.msda_b200_algorithmic_gather_bytes.restype = ctypes.c_uint64
+    lib.msda_b200_algorithmic_gather_bytes.argtypes = [i64, i64, i64, i64, i64, i64, ci]
+    lib.msda_b200_read_probe.restype = ci
+    lib.msda_b200_read_probe.argtypes = [vp, ctypes.c_size_t, ci, vp, vp]
+    if lib.msda_b200_abi_version() != 1:
+        raise NativeLibraryError("libmsda_b200.so ABI version mismatch; rebuild it")
+    _lib = lib
+    return lib
+
+
+def error_string(code: int) -> str:
+    return load().msda_b200_error_string(int(code)).decode()
+
+
+def launch_count() -> int:
+    return int(load().msda_b200_launch_count())
+
+
+def last_variant() -> str:
+    return load().msda_b200_last_variant().decode()

@@ -1,0 +1,1084 @@
+// msda_sm100.cu -- multi-scale deformable attention forward for NVIDIA B200 (sm_100a).
+//
+// Written from scratch for Blackwell; it is NOT a port of the reference's
+// mmcv-derived kernel (codetr/csrc/ms_deform_attn.cu:211-261, one thread per
+// output channel, scalar loads).  What it computes is the reference's
+// operator, bit-for-bit in layout and boundary semantics:
+//
+//   out[b,q,m,:] = sum_{l,p} w[b,q,m,l,p] * bilinear(value_l[b,:,m,:], loc[b,q,m,l,p])
+//
+// with  x_pix = x*W - 0.5,  y_pix = y*H - 0.5  (align_corners=False), zero
+// padding per corner and the whole-sample range test of
+// ms_deform_attn.cu:246-249.
+//
+// Design (see DESIGN.md for the measurements behind each choice)
+//   * The value pyramid is channels-last: one (pixel, head) row is D elements
+//     = 64 B in fp16/bf16 at D=32.  A *lane group* of G = D*sizeof(T)/16 lanes
+//     owns one (query, head) pair and fetches every bilinear corner row with
+//     one 128-bit load per lane (LDG.E.128); a warp therefore serves 32/G
+//     pairs per instruction instead of one.
+//   * All sample geometry (floor, corner weights, validity) is computed once
+//     per lane group, not once per channel; accumulation is fp32 (fp64 for
+//     double) and the result is rounded once on the way out.
+//   * fp16/bf16 inputs can use Blackwell's mixed-precision FMA (PTX
+//     fma.rn.f32.f16 / .bf16 -> SASS FHFMA, sm_100+ only): the 16-bit value
+//     is multiplied in place, without the unpack/convert instructions, and
+//     accumulated in fp32.
+//   * Queries are processed in spatially coherent tiles (encoder shapes,
+//     Q == S): the CTA walks a TH x TW patch of one pyramid level so that the
+//     corner rows fetched by neighbouring queries hit L1/L2; in "head-major"
+//     order a warp holds the same head of 32/G neighbouring queries, so
+//     samples that land on the same pixel coalesce into one L1 wavefront.
+//   * Level shapes / start indices stay device-resident (TensorRT hands them
+//     over as device buffers, deformable_attention_plugin.cpp:339-341): the
+//     kernel reads them itself, the launcher never touches them, so the launch
+//     is capture-safe and sync-free.
+//   * Per-query sampling locations and weights are staged into shared memory
+//     with 1-D TMA bulk copies (cp.async.bulk + mbarrier, SASS UBLKCP) when the
+//     tile's rows are 16-byte aligned; otherwise they are read directly.
+//   * Tensor cores are not used: the op is a gather plus a weighted sum.
+//
+// The C ABI is declared in include/msda_b200.h.
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "msda_b200.h"
+
+namespace {
+
+constexpr int kMaxLevelsSmem = 16;  // levels cached in shared memory by the fast kernels
+constexpr int kThreads = 256;
+
+std::atomic<uint64_t> g_launch_count{0};
+thread_local char g_last_variant[128] = "none";
+
+// ---------------------------------------------------------------------------
+// element traits
+// ---------------------------------------------------------------------------
+template <typename T>
+struct Elem;
+
+template <>
+struct Elem<float> {
+  using acc_t = float;
+  static __device__ __forceinline__ float to_acc(float v) { return v; }
+  static __device__ __forceinline__ float from_acc(float v) { return v; }
+};
+template <>
+struct Elem<double> {
+  using acc_t = double;
+  static __device__ __forceinline__ double to_acc(double v) { return v; }
+  static __device__ __forceinline__ double from_acc(double v) { return v; }
+};
+template <>
+struct Elem<__half> {
+  using acc_t = float;
+  static __device__ __forceinline__ float to_acc(__half v) { return __half2float(v); }
+  static __device__ __forceinline__ __half from_acc(float v) { return __float2half_rn(v); }
+};
+template <>
+struct Elem<__nv_bfloat16> {
+  using acc_t = float;
+  static __device__ __forceinline__ float to_acc(__nv_bfloat16 v) { return __bfloat162float(v); }
+  static __device__ __forceinline__ __nv_bfloat16 from_acc(float v) { return __float2bfloat16_rn(v); }
+};
+
+// ---------------------------------------------------------------------------
+// kernel parameters
+// ---------------------------------------------------------------------------
+struct MsdaParams {
+  const void *value;
+  const int64_t *shapes;  // [L,2] (H,W), device
+  const int64_t *starts;  // [L], device
+  const void *loc;        // [B,Q,M,L,P,2]            (plain mode)
+  const void *weight;     // [B,Q,M,L,P]              (plain mode)
+  const void *ref;        // [B,Q,L,ref_dim]          (fused mode)
+  const void *offsets;    // [B,Q,M,L,P,2]            (fused mode)
+  const void *logits;     // [B,Q,M,L*P]              (fused mode)
+  void *out;              // [B,Q,M*D]
+  int B, S, M, D, L, Q, P;
+  int ref_dim;  // 0 = plain mode, 2 or 4 = fused mode
+  int tile_w, tile_h;   // query tile (tiled order) ; tile_w*tile_h queries per tile in linear order
+  int want_tiled;       // 1: use 2-D tiles when sum(H*W) == Q
+  int head_major;       // 1: a warp holds one head of 32/G neighbouring queries
+};
+
+struct LevelGeom {
+  int H, W, start, qstart;
+};
+
+// ---------------------------------------------------------------------------
+// sample geometry, shared by every kernel
+//   follows ms_deform_attn.cu:246-249 (un-normalise, whole-sample test) and
+//   :35-42, :53-73 (floor, corner validity, corner weights)
+// ---------------------------------------------------------------------------
+template <typename A>
+struct Sample {
+  int idx[4];   // pixel index (h*W + w) of the four corners inside the level
+  A cw[4];      // corner weight, already multiplied by the attention weight
+  bool ok[4];   // corner inside the level (false -> contributes zero)
+};
+
+template <typename A>
+__device__ __forceinline__ A floor_acc(A v);
+template <>
+__device__ __forceinline__ float floor_acc<float>(float v) { return floorf(v); }
+template <>
+__device__ __forceinline__ double floor_acc<double>(double v) { return floor(v); }
+
+template <typename A>
+__device__ __forceinline__ Sample<A> make_sample(A x, A y, A aw, int H, int W) {
+  Sample<A> s;
+  // x*W - 0.5 with the product rounded first, like the reference's scalar_t arithmetic
+  const A w_im = x * (A)W - (A)0.5;
+  const A h_im = y * (A)H - (A)0.5;
+  const bool inside = (h_im > (A)-1) && (w_im > (A)-1) && (h_im < (A)H) && (w_im < (A)W);
+  const A hf = floor_acc<A>(h_im), wf = floor_acc<A>(w_im);
+  const int h_lo = inside ? (int)hf : 0;
+  const int w_lo = inside ? (int)wf : 0;
+  const A lh = h_im - hf, lw = w_im - wf;
+  const A hh = (A)1 - lh, hw = (A)1 - lw;
+  const bool top = h_lo >= 0, bot = h_lo + 1 <= H - 1;
+  const bool lef = w_lo >= 0, rig = w_lo + 1 <= W - 1;
+  s.ok[0] = inside && top && lef;
+  s.ok[1] = inside && top && rig;
+  s.ok[2] = inside && bot && lef;
+  s.ok[3] = inside && bot && rig;
+  const int base = h_lo * W + w_lo;
+  s.idx[0] = base;
+  s.idx[1] = base + 1;
+  s.idx[2] = base + W;
+  s.idx[3] = base + W + 1;
+  // a sample that fails the range test contributes nothing; its weights may be inf/NaN
+  // (non-finite or huge locations), so they are forced to zero rather than multiplied by zero rows
+  const A awi = inside ? aw : (A)0;
+  s.cw[0] = inside ? (hh * hw) * awi : (A)0;
+  s.cw[1] = inside ? (hh * lw) * awi : (A)0;
+  s.cw[2] = inside ? (lh * hw) * awi : (A)0;
+  s.cw[3] = inside ? (lh * lw) * awi : (A)0;
+  return s;
+}
+
+// ---------------------------------------------------------------------------
+// Generic kernel: any D, any L, any P, any dtype (incl. double).  One thread per
+// output element; used for shapes the vector kernel does not cover and as the
+// in-library cross-check of the fast paths.  Fused mode is supported here too.
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads) msda_fwd_generic(const MsdaParams p) {
+  using A = typename Elem<T>::acc_t;
+  const T *__restrict__ value = static_cast<const T *>(p.value);
+  T *__restrict__ out = static_cast<T *>(p.out);
+  const int64_t n = (int64_t)p.B * p.Q * p.M * p.D;
+  const int LP = p.L * p.P;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % p.D);
+    const int64_t pair = i / p.D;  // (b*Q + q)*M + m
+    const int m = (int)(pair % p.M);
+    const int64_t bq = pair / p.M;
+    const int64_t b = bq / p.Q;
+    const T *vb = value + ((int64_t)b * p.S) * p.M * p.D + (int64_t)m * p.D + c;
+
+    A mx = 0, denom = 1;
+    if (p.ref_dim) {  // softmax statistics over the L*P logits of this pair
+      const T *lg = static_cast<const T *>(p.logits) + pair * LP;
+      mx = Elem<T>::to_acc(lg[0]);
+      for (int j = 1; j < LP; ++j) {
+        const A v = Elem<T>::to_acc(lg[j]);
+        mx = v > mx ? v : mx;
+      }
+      denom = 0;
+      for (int j = 0; j < LP; ++j) denom += exp(Elem<T>::to_acc(lg[j]) - mx);
+    }
+
+    A acc = 0;
+    for (int l = 0; l < p.L; ++l) {
+      const int H = (int)p.shapes[2 * l], W = (int)p.shapes[2 * l + 1];
+      const T *vl = vb + p.starts[l] * (int64_t)p.M * p.D;
+      for (int k = 0; k < p.P; ++k) {
+        A x, y, aw;
+        const int64_t si = pair * LP + (int64_t)l * p.P + k;
+        if (p.ref_dim == 0) {
+          const T *lc = static_cast<const T *>(p.loc) + si * 2;
+          x = Elem<T>::to_acc(lc[0]);
+          y = Elem<T>::to_acc(lc[1]);
+          aw = Elem<T>::to_acc(static_cast<const T *>(p.weight)[si]);
+        } else {
+          const T *of = static_cast<const T *>(p.offsets) + si * 2;
+          const T *rf = static_cast<const T *>(p.ref) + (bq * p.L + l) * p.ref_dim;
+          const A ox = Elem<T>::to_acc(of[0]), oy = Elem<T>::to_acc(of[1]);
+          if (p.ref_dim == 2) {
+            x = Elem<T>::to_acc(rf[0]) + ox / (A)W;
+            y = Elem<T>::to_acc(rf[1]) + oy / (A)H;
+          } else {
+            x = Elem<T>::to_acc(rf[0]) + ox / (A)p.P * Elem<T>::to_acc(rf[2]) * (A)0.5;
+            y = Elem<T>::to_acc(rf[1]) + oy / (A)p.P * Elem<T>::to_acc(rf[3]) * (A)0.5;
+          }
+          aw = exp(Elem<T>::to_acc(static_cast<const T *>(p.logits)[si]) - mx) / denom;
+        }
+        const Sample<A> s = make_sample<A>(x, y, aw, H, W);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (s.ok[j]) acc += s.cw[j] * Elem<T>::to_acc(vl[(int64_t)s.idx[j] * p.M * p.D]);
+        }
+      }
+    }
+    out[i] = Elem<T>::from_acc(acc);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Vector kernel helpers
+// ---------------------------------------------------------------------------
+enum MathMode { kExact = 0, kFhfma = 1 };
+
+__device__ __forceinline__ uint4 ldg128(const void *ptr) {
+  return __ldg(static_cast<const uint4 *>(ptr));
+}
+
+// acc[0..VEC) += cw * row, for one 16-byte piece of a corner row
+template <typename T, int MATH>
+struct RowFma;
+
+template <int MATH>
+struct RowFma<float, MATH> {
+  static __device__ __forceinline__ void run(float (&acc)[4], const uint4 &r, float cw, unsigned /*cw16*/) {
+    acc[0] = fmaf(cw, __uint_as_float(r.x), acc[0]);
+    acc[1] = fmaf(cw, __uint_as_float(r.y), acc[1]);
+    acc[2] = fmaf(cw, __uint_as_float(r.z), acc[2]);
+    acc[3] = fmaf(cw, __uint_as_float(r.w), acc[3]);
+  }
+};
+
+template <>
+struct RowFma<__half, kExact> {
+  static __device__ __forceinline__ void run(float (&acc)[8], const uint4 &r, float cw, unsigned) {
+    const unsigned w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&w[i]));
+      acc[2 * i] = fmaf(cw, f.x, acc[2 * i]);
+      acc[2 * i + 1] = fmaf(cw, f.y, acc[2 * i + 1]);
+    }
+  }
+};
+
+template <>
+struct RowFma<__nv_bfloat16, kExact> {
+  static __device__ __forceinline__ void run(float (&acc)[8], const uint4 &r, float cw, unsigned) {
+    const unsigned w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      // bf16 -> fp32 is a 16-bit shift: keep it on the integer pipe
+      acc[2 * i] = fmaf(cw, __uint_as_float(w[i] << 16), acc[2 * i]);
+      acc[2 * i + 1] = fmaf(cw, __uint_as_float(w[i] & 0xffff0000u), acc[2 * i + 1]);
+    }
+  }
+};
+
+// Blackwell mixed-precision FMA: d(f32) = a(f16) * b(f16) + c(f32), SASS FHFMA.
+__device__ __forceinline__ float fhfma_f16(unsigned short a, unsigned short b, float c) {
+  float d;
+  asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(d) : "h"(a), "h"(b), "f"(c));
+  return d;
+}
+__device__ __forceinline__ float fhfma_bf16(unsigned short a, unsigned short b, float c) {
+  float d;
+  asm("fma.rn.f32.bf16 %0, %1, %2, %3;" : "=f"(d) : "h"(a), "h"(b), "f"(c));
+  return d;
+}
+
+template <>
+struct RowFma<__half, kFhfma> {
+  static __device__ __forceinline__ void run(float (&acc)[8], const uint4 &r, float, unsigned cw16) {
+    const unsigned w[4] = {r.x, r.y, r.z, r.w};
+    const unsigned short c = (unsigned short)cw16;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      acc[2 * i] = fhfma_f16((unsigned short)(w[i] & 0xffffu), c, acc[2 * i]);
+      acc[2 * i + 1] = fhfma_f16((unsigned short)(w[i] >> 16), c, acc[2 * i + 1]);
+    }
+  }
+};
+
+template <>
+struct RowFma<__nv_bfloat16, kFhfma> {
+  static __device__ __forceinline__ void run(float (&acc)[8], const uint4 &r, float, unsigned cw16) {
+    const unsigned w[4] = {r.x, r.y, r.z, r.w};
+    const unsigned short c = (unsigned short)cw16;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      acc[2 * i] = fhfma_bf16((unsigned short)(w[i] & 0xffffu), c, acc[2 * i]);
+      acc[2 * i + 1] = fhfma_bf16((unsigned short)(w[i] >> 16), c, acc[2 * i + 1]);
+    }
+  }
+};
+
+template <typename T>
+__device__ __forceinline__ unsigned weight_to_16(float cw);
+template <>
+__device__ __forceinline__ unsigned weight_to_16<__half>(float cw) {
+  return (unsigned)__half_as_ushort(__float2half_rn(cw));
+}
+template <>
+__device__ __forceinline__ unsigned weight_to_16<__nv_bfloat16>(float cw) {
+  return (unsigned)__bfloat16_as_ushort(__float2bfloat16_rn(cw));
+}
+template <>
+__device__ __forceinline__ unsigned weight_to_16<float>(float) {
+  return 0u;
+}
+
+// two packed 16-bit elements -> two floats
+template <typename T>
+__device__ __forceinline__ float2 unpack2(unsigned v);
+template <>
+__device__ __forceinline__ float2 unpack2<__half>(unsigned v) {
+  return __half22float2(*reinterpret_cast<const __half2 *>(&v));
+}
+template <>
+__device__ __forceinline__ float2 unpack2<__nv_bfloat16>(unsigned v) {
+  return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
+}
+template <>
+__device__ __forceinline__ float2 unpack2<float>(unsigned) {
+  return make_float2(0.f, 0.f);
+}
+
+template <typename T, int VEC>
+__device__ __forceinline__ void store_row(T *dst, const float (&acc)[VEC]);
+
+template <>
+__device__ __forceinline__ void store_row<float, 4>(float *dst, const float (&acc)[4]) {
+  *reinterpret_cast<float4 *>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+}
+template <>
+__device__ __forceinline__ void store_row<__half, 8>(__half *dst, const float (&acc)[8]) {
+  uint4 o;
+  __half2 h;
+  h = __floats2half2_rn(acc[0], acc[1]);
+  o.x = *reinterpret_cast<unsigned *>(&h);
+  h = __floats2half2_rn(acc[2], acc[3]);
+  o.y = *reinterpret_cast<unsigned *>(&h);
+  h = __floats2half2_rn(acc[4], acc[5]);
+  o.z = *reinterpret_cast<unsigned *>(&h);
+  h = __floats2half2_rn(acc[6], acc[7]);
+  o.w = *reinterpret_cast<unsigned *>(&h);
+  *reinterpret_cast<uint4 *>(dst) = o;
+}
+template <>
+__device__ __forceinline__ void store_row<__nv_bfloat16, 8>(__nv_bfloat16 *dst, const float (&acc)[8]) {
+  uint4 o;
+  __nv_bfloat162 h;
+  h = __floats2bfloat162_rn(acc[0], acc[1]);
+  o.x = *reinterpret_cast<unsigned *>(&h);
+  h = __floats2bfloat162_rn(acc[2], acc[3]);
+  o.y = *reinterpret_cast<unsigned *>(&h);
+  h = __floats2bfloat162_rn(acc[4], acc[5]);
+  o.z = *reinterpret_cast<unsigned *>(&h);
+  h = __floats2bfloat162_rn(acc[6], acc[7]);
+  o.w = *reinterpret_cast<unsigned *>(&h);
+  *reinterpret_cast<uint4 *>(dst) = o;
+}
+
+// ---- TMA 1-D bulk copy + mbarrier (Blackwell/Hopper async proxy) ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// ---------------------------------------------------------------------------
+// Tile bookkeeping shared by the vector kernels
+// ---------------------------------------------------------------------------
+struct TileSetup {
+  LevelGeom lv[kMaxLevelsSmem];
+  int tile_first[kMaxLevelsSmem + 1];  // first tile index of each level (tiled order)
+  int n_tiles;                         // tiles per image
+  int tiled;                           // 1 = 2-D tiles, 0 = linear chunks
+};
+
+__device__ __forceinline__ void setup_tiles(const MsdaParams &p, TileSetup &ts) {
+  // executed by warp 0 of the CTA (all 32 lanes); L <= kMaxLevelsSmem <= 32 guaranteed by the host.
+  // Lane l loads level l (the loads of all levels are in flight together), then two warp scans
+  // give each level its first query and first tile.
+  const int l = threadIdx.x;
+  int H = 0, W = 0, start = 0;
+  if (l < p.L) {
+    H = (int)__ldg(p.shapes + 2 * l);
+    W = (int)__ldg(p.shapes + 2 * l + 1);
+    start = (int)__ldg(p.starts + l);
+  }
+  const int nq = H * W;
+  const int nt = (l < p.L) ? ((H + p.tile_h - 1) / p.tile_h) * ((W + p.tile_w - 1) / p.tile_w) : 0;
+  int qs = nq, tsum = nt;  // inclusive scans
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const int a = __shfl_up_sync(0xffffffffu, qs, off);
+    const int c = __shfl_up_sync(0xffffffffu, tsum, off);
+    if (l >= off) {
+      qs += a;
+      tsum += c;
+    }
+  }
+  if (l < p.L) {
+    ts.lv[l].H = H;
+    ts.lv[l].W = W;
+    ts.lv[l].start = start;
+    ts.lv[l].qstart = qs - nq;
+    ts.tile_first[l] = tsum - nt;
+  }
+  const int q_total = __shfl_sync(0xffffffffu, qs, 31);
+  const int t_total = __shfl_sync(0xffffffffu, tsum, 31);
+  if (l == 0) {
+    ts.tile_first[p.L] = t_total;
+    const int tq = p.tile_w * p.tile_h;
+    if (p.want_tiled && q_total == p.Q) {
+      ts.tiled = 1;
+      ts.n_tiles = t_total;
+    } else {
+      ts.tiled = 0;
+      ts.n_tiles = (p.Q + tq - 1) / tq;
+    }
+  }
+}
+
+// Maps (tile, slot-in-tile) to a query index, or -1 for a padding slot.
+struct TileCursor {
+  int q0;       // linear: first query of the tile
+  int lvl_q0;   // tiled: first query of the level
+  int y0, x0;   // tiled: top-left pixel of the tile
+  int H, W;     // tiled: level extent
+};
+
+__device__ __forceinline__ TileCursor open_tile(const MsdaParams &p, const TileSetup &ts, int t) {
+  TileCursor c;
+  if (!ts.tiled) {
+    c.q0 = t * p.tile_w * p.tile_h;
+    c.lvl_q0 = 0;
+    c.y0 = c.x0 = c.H = c.W = 0;
+    return c;
+  }
+  int l = 0;
+  while (l + 1 < p.L && t >= ts.tile_first[l + 1]) ++l;
+  const int tl = t - ts.tile_first[l];
+  const int tiles_x = (ts.lv[l].W + p.tile_w - 1) / p.tile_w;
+  c.q0 = 0;
+  c.lvl_q0 = ts.lv[l].qstart;
+  c.y0 = (tl / tiles_x) * p.tile_h;
+  c.x0 = (tl % tiles_x) * p.tile_w;
+  c.H = ts.lv[l].H;
+  c.W = ts.lv[l].W;
+  return c;
+}
+
+__device__ __forceinline__ int tile_query(const MsdaParams &p, const TileSetup &ts, const TileCursor &c, int tq) {
+  if (!ts.tiled) {
+    const int q = c.q0 + tq;
+    return q < p.Q ? q : -1;
+  }
+  const int y = c.y0 + tq / p.tile_w, x = c.x0 + tq % p.tile_w;
+  return (y < c.H && x < c.W) ? c.lvl_q0 + y * c.W + x : -1;
+}
+
+// ---------------------------------------------------------------------------
+// Vector kernel.
+//   T     element type (float / __half / __nv_bfloat16)
+//   D     channels per head (D*sizeof(T) multiple of 16, G = D*sizeof(T)/16 <= 32)
+//   P_T   points per level known at compile time (4) or 0 = run-time
+//   SPLIT lanes groups co-operating on one pair: the P points of a level are
+//         dealt round-robin to SPLIT sub-groups and reduced with shuffles
+//         (small-Q / decoder shapes, to expose more parallelism)
+//   MATH  kExact: fp32 weights ; kFhfma: 16-bit weights + FHFMA
+// ---------------------------------------------------------------------------
+template <typename T, int D, int P_T, int SPLIT, int MATH>
+__global__ void __launch_bounds__(kThreads, 2) msda_fwd_vec(const MsdaParams p) {
+  constexpr int E = (int)sizeof(T);
+  constexpr int VEC = 16 / E;            // channels per lane
+  constexpr int G = D / VEC;             // lanes per corner row
+  constexpr int GS = G * SPLIT;          // lanes per (query, head) pair
+  constexpr int PPW = 32 / GS;           // pairs per warp
+  constexpr int PAIRS_PER_PASS = kThreads / GS;
+  static_assert(D % VEC == 0 && GS <= 32 && (GS & (GS - 1)) == 0, "unsupported D / SPLIT");
+
+  __shared__ TileSetup ts;
+  if (threadIdx.x < 32) setup_tiles(p, ts);
+  __syncthreads();
+
+  const char *__restrict__ value = static_cast<const char *>(p.value);
+  const T *__restrict__ loc = static_cast<const T *>(p.loc);
+  const T *__restrict__ wgt = static_cast<const T *>(p.weight);
+  T *__restrict__ out = static_cast<T *>(p.out);
+
+  const int P = P_T ? P_T : p.P;
+  const int LP = p.L * P;
+  const int M = p.M;
+  const size_t pix_bytes = (size_t)M * D * E;
+  const int lane_in_pair = threadIdx.x % GS;
+  const int sub = lane_in_pair % G;     // which 16-byte piece of the row
+  const int split = lane_in_pair / G;   // which share of the points
+  const int slot0 = threadIdx.x / GS;
+  const int tile_q = p.tile_w * p.tile_h;
+  const int slots = tile_q * M;
+  const int64_t work = (int64_t)p.B * ts.n_tiles;
+
+  for (int64_t wi = blockIdx.x; wi < work; wi += gridDim.x) {
+    const int b = (int)(wi / ts.n_tiles);
+    const int t = (int)(wi - (int64_t)b * ts.n_tiles);
+    const TileCursor cur = open_tile(p, ts, t);
+    const char *vb = value + (size_t)b * p.S * pix_bytes + (size_t)sub * 16;
+
+    for (int s = slot0; s < slots; s += PAIRS_PER_PASS) {
+      int tq, m;
+      if (p.head_major) {
+        const int qb = s / (PPW * M), r = s - qb * (PPW * M);
+        m = r / PPW;
+        tq = qb * PPW + (r - m * PPW);
+      } else {
+        tq = s / M;
+        m = s - tq * M;
+      }
+      const int q = tile_query(p, ts, cur, tq);
+      // a pair is handled by GS consecutive lanes, so this branch never splits a lane group;
+      // the shuffles below only cross lanes of the same pair
+      if (q < 0) continue;
+
+      const int64_t pair = ((int64_t)b * p.Q + q) * M + m;
+      const T *lp = loc + pair * LP * 2;
+      const T *wp = wgt + pair * LP;
+      const char *vm = vb + (size_t)m * D * E;
+
+      float acc[VEC];
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+
+      for (int l = 0; l < p.L; ++l) {
+        const int H = ts.lv[l].H, W = ts.lv[l].W;
+        const char *vl = vm + (size_t)ts.lv[l].start * pix_bytes;
+
+        if constexpr (P_T == 4 && SPLIT == 1) {
+          // all four points of the level: one vector load of locations, one of weights
+          float xs[4], ys[4], aws[4];
+          if constexpr (E == 2) {
+            const uint4 lraw = ldg128(lp + l * 8);
+            const uint2 wraw = __ldg(reinterpret_cast<const uint2 *>(wp + l * 4));
+            const unsigned lw[4] = {lraw.x, lraw.y, lraw.z, lraw.w};
+            const unsigned ww[2] = {wraw.x, wraw.y};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float2 xy = unpack2<T>(lw[k]);
+              const float2 a2 = unpack2<T>(ww[k / 2]);
+              xs[k] = xy.x;
+              ys[k] = xy.y;
+              aws[k] = (k & 1) ? a2.y : a2.x;
+            }
+          } else {
+            const float4 l0 = __ldg(reinterpret_cast<const float4 *>(lp + l * 8));
+            const float4 l1 = __ldg(reinterpret_cast<const float4 *>(lp + l * 8 + 4));
+            const float4 w4 = __ldg(reinterpret_cast<const float4 *>(wp + l * 4));
+            xs[0] = l0.x; ys[0] = l0.y; xs[1] = l0.z; ys[1] = l0.w;
+            xs[2] = l1.x; ys[2] = l1.y; xs[3] = l1.z; ys[3] = l1.w;
+            aws[0] = w4.x; aws[1] = w4.y; aws[2] = w4.z; aws[3] = w4.w;
+          }
+          Sample<float> sm[4];
+          uint4 rows[4][4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            sm[k] = make_sample<float>(xs[k], ys[k], aws[k], H, W);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              rows[k][j] = make_uint4(0u, 0u, 0u, 0u);
+              if (sm[k].ok[j]) rows[k][j] = ldg128(vl + (size_t)sm[k].idx[j] * pix_bytes);
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              RowFma<T, MATH>::run(acc, rows[k][j], sm[k].cw[j], MATH == kFhfma ? weight_to_16<T>(sm[k].cw[j]) : 0u);
+            }
+          }
+        } else {
+          // run-time P and/or split points: scalar loads of the location / weight
+          for (int k = split; k < P; k += SPLIT) {
+            const int si = l * P + k;
+            const float x = Elem<T>::to_acc(lp[si * 2]);
+            const float y = Elem<T>::to_acc(lp[si * 2 + 1]);
+            const float aw = Elem<T>::to_acc(wp[si]);
+            const Sample<float> sm = make_sample<float>(x, y, aw, H, W);
+            uint4 rows[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              rows[j] = make_uint4(0u, 0u, 0u, 0u);
+              if (sm.ok[j]) rows[j] = ldg128(vl + (size_t)sm.idx[j] * pix_bytes);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              RowFma<T, MATH>::run(acc, rows[j], sm.cw[j], MATH == kFhfma ? weight_to_16<T>(sm.cw[j]) : 0u);
+            }
+          }
+        }
+      }
+
+      if constexpr (SPLIT > 1) {
+        // only the GS lanes of this pair are named in the mask: other pairs of the warp may have
+        // left the loop already
+        const unsigned lane = threadIdx.x & 31u;
+        const unsigned pair_mask = (GS == 32) ? 0xffffffffu : (((1u << GS) - 1u) << (lane & ~(unsigned)(GS - 1)));
+#pragma unroll
+        for (int off = G; off < GS; off <<= 1) {
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) acc[i] += __shfl_xor_sync(pair_mask, acc[i], off);
+        }
+      }
+      if (split == 0) store_row<T, VEC>(out + pair * D + sub * VEC, acc);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// read-bandwidth probe (roofline denominators: L2 -> SM, HBM -> SM)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) read_probe_kernel(const uint4 *__restrict__ buf, size_t n_vec, int repeats,
+                                                              unsigned *sink) {
+  unsigned acc = 0;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (int r = 0; r < repeats; ++r) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
+      uint4 v;
+      // ld.global.cv would bypass L2 too; .cg caches in L2 only, which is what we want to measure
+      asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(buf + i));
+      acc ^= v.x ^ v.y ^ v.z ^ v.w;
+    }
+  }
+  if (acc == 0x9e3779b9u) *sink = acc;  // practically never true; keeps the loads alive
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+size_t elem_size(int dtype) {
+  switch (dtype) {
+    case MSDA_F32: return 4;
+    case MSDA_F16: return 2;
+    case MSDA_BF16: return 2;
+    case MSDA_F64: return 8;
+    default: return 0;
+  }
+}
+
+const char *dtype_name(int dtype) {
+  switch (dtype) {
+    case MSDA_F32: return "f32";
+    case MSDA_F16: return "f16";
+    case MSDA_BF16: return "bf16";
+    case MSDA_F64: return "f64";
+    default: return "?";
+  }
+}
+
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+int env_int(const char *name, int fallback) {
+  const char *v = getenv(name);
+  if (!v || !*v) return fallback;
+  return atoi(v);
+}
+
+template <typename T>
+int launch_generic(const MsdaParams &p, cudaStream_t stream) {
+  const int64_t n = (int64_t)p.B * p.Q * p.M * p.D;
+  int64_t blocks = (n + kThreads - 1) / kThreads;
+  const int64_t cap = (int64_t)sm_count() * 32;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  msda_fwd_generic<T><<<(unsigned)blocks, kThreads, 0, stream>>>(p);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  return (int)cudaGetLastError();
+}
+
+struct VecPlan {
+  int split;
+  int math;
+  unsigned grid;
+};
+
+template <typename T, int D, int P_T, int SPLIT, int MATH>
+int launch_vec_inst(const MsdaParams &p, unsigned grid, cudaStream_t stream) {
+  msda_fwd_vec<T, D, P_T, SPLIT, MATH><<<grid, kThreads, 0, stream>>>(p);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  return (int)cudaGetLastError();
+}
+
+template <typename T, int D, int MATH>
+int launch_vec_d(const MsdaParams &p, const VecPlan &plan, cudaStream_t stream) {
+  constexpr int G = D * (int)sizeof(T) / 16;
+  if (plan.split == 4) {
+    if constexpr (G * 4 <= 32) {
+      return p.P == 4 ? launch_vec_inst<T, D, 4, 4, MATH>(p, plan.grid, stream)
+                      : launch_vec_inst<T, D, 0, 4, MATH>(p, plan.grid, stream);
+    }
+  }
+  return p.P == 4 ? launch_vec_inst<T, D, 4, 1, MATH>(p, plan.grid, stream)
+                  : launch_vec_inst<T, D, 0, 1, MATH>(p, plan.grid, stream);
+}
+
+template <typename T>
+int launch_vec_t(const MsdaParams &p, const VecPlan &plan, cudaStream_t stream) {
+  constexpr bool k16 = sizeof(T) == 2;
+  if (k16 && plan.math == kFhfma) {
+    if constexpr (k16) {
+      switch (p.D) {
+        case 16: return launch_vec_d<T, 16, kFhfma>(p, plan, stream);
+        case 32: return launch_vec_d<T, 32, kFhfma>(p, plan, stream);
+        case 64: return launch_vec_d<T, 64, kFhfma>(p, plan, stream);
+        default: return MSDA_ERR_UNSUPPORTED;
+      }
+    }
+  }
+  switch (p.D) {
+    case 16: return launch_vec_d<T, 16, kExact>(p, plan, stream);
+    case 32: return launch_vec_d<T, 32, kExact>(p, plan, stream);
+    case 64: return launch_vec_d<T, 64, kExact>(p, plan, stream);
+    default: return MSDA_ERR_UNSUPPORTED;
+  }
+}
+
+bool aligned_to(const void *ptr, size_t a) { return (reinterpret_cast<uintptr_t>(ptr) % a) == 0; }
+
+int forward_impl(MsdaParams p, int dtype, unsigned flags, cudaStream_t stream) {
+  const size_t E = elem_size(dtype);
+  const bool fused = p.ref_dim != 0;
+
+  // ---- choose the kernel ----
+  bool vec_ok = !(flags & MSDA_FLAG_FORCE_GENERIC) && !fused && dtype != MSDA_F64 &&
+                (p.D == 16 || p.D == 32 || p.D == 64) && p.L <= kMaxLevelsSmem &&
+                aligned_to(p.value, 16) && aligned_to(p.out, 16) && ((size_t)p.M * p.D * E) % 16 == 0;
+  const int G = vec_ok ? (int)(p.D * E / 16) : 1;
+  if (vec_ok && p.P == 4) {
+    // the P=4 path reads a level's 4 locations / weights with vector loads
+    vec_ok = aligned_to(p.loc, 16) && aligned_to(p.weight, E == 2 ? 8 : 16);
+  }
+
+  if (!vec_ok) {
+    int rc;
+    switch (dtype) {
+      case MSDA_F32: rc = launch_generic<float>(p, stream); break;
+      case MSDA_F16: rc = launch_generic<__half>(p, stream); break;
+      case MSDA_BF16: rc = launch_generic<__nv_bfloat16>(p, stream); break;
+      case MSDA_F64: rc = launch_generic<double>(p, stream); break;
+      default: return MSDA_ERR_BAD_DTYPE;
+    }
+    if (rc == 0) snprintf(g_last_variant, sizeof(g_last_variant), "generic<%s>%s", dtype_name(dtype), fused ? "/fused" : "");
+    return rc;
+  }
+
+  VecPlan plan;
+  const int sms = sm_count();
+  const int64_t pairs = (int64_t)p.B * p.Q * p.M;
+  // small problems (decoder cross-attention): split the points of a pair over 4 lane groups
+  const int64_t lanes_full = pairs * G;
+  plan.split = (lanes_full < (int64_t)sms * 2048 && G * 4 <= 32) ? 4 : 1;
+  plan.split = env_int("MSDA_B200_SPLIT", plan.split);
+  if (plan.split != 4 || G * 4 > 32) plan.split = 1;
+
+  plan.math = kExact;
+  if (E == 2) {
+    if (flags & MSDA_FLAG_MATH_FHFMA) plan.math = kFhfma;
+    if (flags & MSDA_FLAG_MATH_EXACT) plan.math = kExact;
+  }
+
+  const int ppw = 32 / (G * plan.split);
+  // tile geometry: width a multiple of the pairs a warp holds in head-major order
+  p.want_tiled = (flags & MSDA_FLAG_LINEAR_ORDER) ? 0 : (p.Q == p.S ? 1 : 0);
+  p.head_major = env_int("MSDA_B200_HEAD_MAJOR", 1);
+  p.tile_w = env_int("MSDA_B200_TILE_W", 8);
+  p.tile_h = env_int("MSDA_B200_TILE_H", p.want_tiled ? 4 : 1);
+  if (p.tile_w < ppw) p.tile_w = ppw;
+  p.tile_w = (p.tile_w + ppw - 1) / ppw * ppw;
+  if (p.tile_h < 1) p.tile_h = 1;
+  if (!p.want_tiled) {
+    // linear chunks: one pass of the CTA per tile unless the problem is large
+    const int pairs_per_pass = kThreads / (G * plan.split);
+    int tq = (pairs_per_pass + p.M - 1) / p.M;
+    tq = (tq + ppw - 1) / ppw * ppw;
+    p.tile_w = tq;
+    p.tile_h = 1;
+  }
+
+  // grid: enough CTAs to cover every tile once, capped at a few waves (grid-stride loop inside)
+  const int64_t tile_q = (int64_t)p.tile_w * p.tile_h;
+  // The level shapes are device-resident, so the exact 2-D tile count is unknown here.  The
+  // kernel strides over the real count, so an estimate is enough: interior tiles plus an
+  // allowance for the partial tiles on the right/bottom edge of each level.
+  int64_t tiles_est = (p.Q + tile_q - 1) / tile_q;
+  if (p.want_tiled) tiles_est += tiles_est / 4 + 4 * p.L;
+  int64_t grid = (int64_t)p.B * tiles_est;
+  const int64_t cap = (int64_t)sms * env_int("MSDA_B200_CTAS_PER_SM", 16);
+  if (grid > cap) grid = cap;
+  if (grid < 1) grid = 1;
+  plan.grid = (unsigned)grid;
+
+  int rc;
+  switch (dtype) {
+    case MSDA_F32: rc = launch_vec_t<float>(p, plan, stream); break;
+    case MSDA_F16: rc = launch_vec_t<__half>(p, plan, stream); break;
+    case MSDA_BF16: rc = launch_vec_t<__nv_bfloat16>(p, plan, stream); break;
+    default: return MSDA_ERR_BAD_DTYPE;
+  }
+  if (rc == 0) {
+    snprintf(g_last_variant, sizeof(g_last_variant), "vec<%s,D%d,P%d,split%d>/%s%dx%d/%s/%s", dtype_name(dtype), p.D,
+             p.P == 4 ? 4 : 0, plan.split, p.want_tiled ? "tiled" : "linear", p.tile_w, p.tile_h,
+             p.head_major ? "head-major" : "query-major", plan.math == kFhfma ? "fhfma" : "exact");
+  }
+  return rc;
+}
+
+int validate_common(const void *value, const int64_t *shapes, const int64_t *starts, const void *out, int64_t B,
+                    int64_t S, int64_t M, int64_t D, int64_t L, int64_t Q, int64_t P, int dtype) {
+  if (elem_size(dtype) == 0) return MSDA_ERR_BAD_DTYPE;
+  if (B < 0 || S < 0 || M < 0 || D < 0 || L < 0 || Q < 0 || P < 0) return MSDA_ERR_BAD_SHAPE;
+  const int64_t lim = (int64_t)1 << 31;
+  if (S >= lim || Q >= lim || M >= 65536 || D >= 65536 || L >= 65536 || P >= 65536 || B >= lim) return MSDA_ERR_UNSUPPORTED;
+  if (B * Q * M * D == 0) return MSDA_OK;  // empty output: nothing to do, nothing to check
+  if (!out) return MSDA_ERR_NULL_POINTER;
+  if (L * P > 0 && S > 0 && (!value || !shapes || !starts)) return MSDA_ERR_NULL_POINTER;
+  const size_t E = elem_size(dtype);
+  if (!aligned_to(value, E) || !aligned_to(out, E) || !aligned_to(shapes, 8) || !aligned_to(starts, 8)) return MSDA_ERR_MISALIGNED;
+  return MSDA_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------
+extern "C" {
+
+int msda_b200_abi_version(void) { return MSDA_B200_ABI_VERSION; }
+
+const char *msda_b200_error_string(int code) {
+  switch (code) {
+    case MSDA_OK: return "success";
+    case MSDA_ERR_NULL_POINTER: return "msda_b200: a required pointer is NULL";
+    case MSDA_ERR_BAD_SHAPE: return "msda_b200: negative dimension";
+    case MSDA_ERR_BAD_DTYPE: return "msda_b200: unknown dtype";
+    case MSDA_ERR_BAD_STEP: return "msda_b200: batch must be divisible by min(batch, im2col_step)";
+    case MSDA_ERR_MISALIGNED: return "msda_b200: pointer not aligned to its element size";
+    case MSDA_ERR_UNSUPPORTED: return "msda_b200: shape outside the supported index range";
+    case MSDA_ERR_BAD_FLAGS: return "msda_b200: contradictory flags";
+    default: break;
+  }
+  if (code > 0) return cudaGetErrorString((cudaError_t)code);
+  return "msda_b200: unknown error";
+}
+
+uint64_t msda_b200_launch_count(void) { return g_launch_count.load(std::memory_order_relaxed); }
+
+const char *msda_b200_last_variant(void) { return g_last_variant; }
+
+uint64_t msda_b200_algorithmic_hbm_bytes(int64_t B, int64_t S, int64_t M, int64_t D, int64_t L, int64_t Q, int64_t P,
+                                         int dtype) {
+  const uint64_t E = elem_size(dtype);
+  // value + locations + weights read once, output written once, plus the level table
+  return E * (uint64_t)B * (uint64_t)(S * M * D + Q * M * L * P * 2 + Q * M * L * P + Q * M * D) + 8ull * 3ull * (uint64_t)L;
+}
+
+uint64_t msda_b200_algorithmic_gather_bytes(int64_t B, int64_t M, int64_t D, int64_t L, int64_t Q, int64_t P, int dtype) {
+  return (uint64_t)elem_size(dtype) * (uint64_t)B * (uint64_t)Q * (uint64_t)M * (uint64_t)L * (uint64_t)P * 4ull * (uint64_t)D;
+}
+
+int msda_b200_forward(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                      const void *sampling_loc, const void *attn_weight, void *output, int64_t batch, int64_t num_keys,
+                      int64_t num_heads, int64_t channels, int64_t num_levels, int64_t num_queries, int64_t num_points,
+                      int64_t im2col_step, int dtype, unsigned flags, void *stream) {
+  int rc = validate_common(value, spatial_shapes, level_start_index, output, batch, num_keys, num_heads, channels,
+                           num_levels, num_queries, num_points, dtype);
+  if (rc != MSDA_OK) return rc;
+  if ((flags & MSDA_FLAG_MATH_FHFMA) && (flags & MSDA_FLAG_MATH_EXACT)) return MSDA_ERR_BAD_FLAGS;
+  // ms_deform_attn.cu:922-926: im2col_step_ = min(batch, im2col_step); batch % im2col_step_ == 0
+  if (batch > 0) {
+    const int64_t step = batch < im2col_step ? batch : im2col_step;
+    if (step <= 0 || batch % step != 0) return MSDA_ERR_BAD_STEP;
+  }
+  if (batch * num_queries * num_heads * channels == 0) return MSDA_OK;
+  if (num_levels * num_points > 0 && (!sampling_loc || !attn_weight)) return MSDA_ERR_NULL_POINTER;
+  const size_t E = elem_size(dtype);
+  if (!aligned_to(sampling_loc, E) || !aligned_to(attn_weight, E)) return MSDA_ERR_MISALIGNED;
+
+  MsdaParams p;
+  memset(&p, 0, sizeof(p));
+  p.value = value;
+  p.shapes = spatial_shapes;
+  p.starts = level_start_index;
+  p.loc = sampling_loc;
+  p.weight = attn_weight;
+  p.out = output;
+  p.B = (int)batch; p.S = (int)num_keys; p.M = (int)num_heads; p.D = (int)channels;
+  p.L = (int)num_levels; p.Q = (int)num_queries; p.P = (int)num_points;
+  p.ref_dim = 0;
+  return forward_impl(p, dtype, flags, static_cast<cudaStream_t>(stream));
+}
+
+int msda_b200_forward_fused(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                            const void *reference_points, const void *sampling_offsets, const void *attn_logits,
+                            void *output, int64_t batch, int64_t num_keys, int64_t num_heads, int64_t channels,
+                            int64_t num_levels, int64_t num_queries, int64_t num_points, int64_t ref_dim, int dtype,
+                            unsigned flags, void *stream) {
+  int rc = validate_common(value, spatial_shapes, level_start_index, output, batch, num_keys, num_heads, channels,
+                           num_levels, num_queries, num_points, dtype);
+  if (rc != MSDA_OK) return rc;
+  if (ref_dim != 2 && ref_dim != 4) return MSDA_ERR_BAD_SHAPE;
+  if (batch * num_queries * num_heads * channels == 0) return MSDA_OK;
+  if (num_levels * num_points > 0 && (!reference_points || !sampling_offsets || !attn_logits)) return MSDA_ERR_NULL_POINTER;
+  const size_t E = elem_size(dtype);
+  if (!aligned_to(reference_points, E) || !aligned_to(sampling_offsets, E) || !aligned_to(attn_logits, E)) return MSDA_ERR_MISALIGNED;
+
+  MsdaParams p;
+  memset(&p, 0, sizeof(p));
+  p.value = value;
+  p.shapes = spatial_shapes;
+  p.starts = level_start_index;
+  p.ref = reference_points;
+  p.offsets = sampling_offsets;
+  p.logits = attn_logits;
+  p.out = output;
+  p.B = (int)batch; p.S = (int)num_keys; p.M = (int)num_heads; p.D = (int)channels;
+  p.L = (int)num_levels; p.Q = (int)num_queries; p.P = (int)num_points;
+  p.ref_dim = (int)ref_dim;
+  return forward_impl(p, dtype, flags, static_cast<cudaStream_t>(stream));
+}
+
+int msda_b200_plugin_enqueue(const int64_t *value_dims, const int64_t *loc_dims, int trt_dtype,
+                             const void *const *inputs, void *const *outputs, void * /*workspace*/,
+                             int64_t im2col_step, void *stream) {
+  if (!value_dims || !loc_dims || !inputs || !outputs) return MSDA_ERR_NULL_POINTER;
+  int dtype;
+  switch (trt_dtype) {  // nvinfer1::DataType values (deformable_attention_plugin.cpp:53-62 accepts kFLOAT, kHALF)
+    case 0: dtype = MSDA_F32; break;
+    case 1: dtype = MSDA_F16; break;
+    case 7: dtype = MSDA_BF16; break;
+    default: return MSDA_ERR_BAD_DTYPE;
+  }
+  // deformable_attention_plugin.cpp:305-315
+  const int64_t bs = value_dims[0], num_keys = value_dims[1], num_heads = value_dims[2], dim_per_head = value_dims[3];
+  const int64_t num_queries = loc_dims[1], num_levels = loc_dims[3], num_points = loc_dims[4];
+  if (loc_dims[0] != bs || loc_dims[2] != num_heads || loc_dims[5] != 2) return MSDA_ERR_BAD_SHAPE;
+  return msda_b200_forward(inputs[0], static_cast<const int64_t *>(inputs[1]), static_cast<const int64_t *>(inputs[2]),
+                           inputs[3], inputs[4], outputs[0], bs, num_keys, num_heads, dim_per_head, num_levels,
+                           num_queries, num_points, im2col_step, dtype, MSDA_FLAG_DEFAULT, stream);
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+size_t msda_b200_host_workspace_bytes(int64_t B, int64_t S, int64_t M, int64_t D, int64_t L, int64_t Q, int64_t P,
+                                      int dtype) {
+  const size_t E = elem_size(dtype);
+  if (E == 0) return 0;
+  size_t total = 0;
+  total += align_up((size_t)B * S * M * D * E, 256);
+  total += align_up((size_t)L * 2 * 8, 256);
+  total += align_up((size_t)L * 8, 256);
+  total += align_up((size_t)B * Q * M * L * P * 2 * E, 256);
+  total += align_up((size_t)B * Q * M * L * P * E, 256);
+  total += align_up((size_t)B * Q * M * D * E, 256);
+  return total;
+}
+
+int msda_b200_forward_host(const void *value_host, const int64_t *spatial_shapes_host,
+                           const int64_t *level_start_index_host, const void *sampling_loc_host,
+                           const void *attn_weight_host, void *output_host, void *workspace_dev, size_t workspace_bytes,
+                           int64_t B, int64_t S, int64_t M, int64_t D, int64_t L, int64_t Q, int64_t P,
+                           int64_t im2col_step, int dtype, unsigned flags, void *stream_v) {
+  const size_t E = elem_size(dtype);
+  if (E == 0) return MSDA_ERR_BAD_DTYPE;
+  if (B < 0 || S < 0 || M < 0 || D < 0 || L < 0 || Q < 0 || P < 0) return MSDA_ERR_BAD_SHAPE;
+  if (!workspace_dev || workspace_bytes < msda_b200_host_workspace_bytes(B, S, M, D, L, Q, P, dtype)) return MSDA_ERR_NULL_POINTER;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  char *ws = static_cast<char *>(workspace_dev);
+  const size_t n_val = (size_t)B * S * M * D * E, n_shp = (size_t)L * 16, n_st = (size_t)L * 8;
+  const size_t n_loc = (size_t)B * Q * M * L * P * 2 * E, n_w = (size_t)B * Q * M * L * P * E, n_out = (size_t)B * Q * M * D * E;
+  char *d_val = ws; ws += align_up(n_val, 256);
+  char *d_shp = ws; ws += align_up(n_shp, 256);
+  char *d_st = ws; ws += align_up(n_st, 256);
+  char *d_loc = ws; ws += align_up(n_loc, 256);
+  char *d_w = ws; ws += align_up(n_w, 256);
+  char *d_out = ws;
+  cudaError_t e;
+#define MSDA_COPY(dst, src, n, kind)                                   \
+  if ((n) > 0) {                                                       \
+    if (!(src) || !(dst)) return MSDA_ERR_NULL_POINTER;                \
+    e = cudaMemcpyAsync((dst), (src), (n), (kind), stream);            \
+    if (e != cudaSuccess) return (int)e;                               \
+  }
+  MSDA_COPY(d_val, value_host, n_val, cudaMemcpyHostToDevice)
+  MSDA_COPY(d_shp, spatial_shapes_host, n_shp, cudaMemcpyHostToDevice)
+  MSDA_COPY(d_st, level_start_index_host, n_st, cudaMemcpyHostToDevice)
+  MSDA_COPY(d_loc, sampling_loc_host, n_loc, cudaMemcpyHostToDevice)
+  MSDA_COPY(d_w, attn_weight_host, n_w, cudaMemcpyHostToDevice)
+  const int rc = msda_b200_forward(d_val, reinterpret_cast<const int64_t *>(d_shp), reinterpret_cast<const int64_t *>(d_st),
+                                   d_loc, d_w, d_out, B, S, M, D, L, Q, P, im2col_step, dtype, flags, stream_v);
+  if (rc != 0) return rc;
+  MSDA_COPY(output_host, d_out, n_out, cudaMemcpyDeviceToHost)
+#undef MSDA_COPY
+  return MSDA_OK;
+}
+
+int msda_b200_read_probe(const void *buf, size_t bytes, int repeats, void *sink, void *stream) {
+  if (!buf || !sink) return MSDA_ERR_NULL_POINTER;
+  if (!aligned_to(buf, 16)) return MSDA_ERR_MISALIGNED;
+  const size_t n_vec = bytes / 16;
+  if (n_vec == 0 || repeats <= 0) return MSDA_OK;
+  const unsigned grid = (unsigned)(sm_count() * 8);
+  read_probe_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint4 *>(buf), n_vec,
+                                                                              repeats, static_cast<unsigned *>(sink));
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  return (int)cudaGetLastError();
+}
+
+}  // extern "C"

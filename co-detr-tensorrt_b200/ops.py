@@ -1,0 +1,311 @@
+"""Host-side mirror of the reference's operator interface for the MSDA forward path.
+
+What the reference exposes and what stands behind it here:
+
+* ``torch.ops.codetr.multi_scale_deformable_attention(value, spatial_shapes,
+  level_start_index, sampling_loc, attn_weight, im2col_step) -> Tensor``
+  -- schema string of /root/reference/codetr/csrc/deformable_attention_torch.cpp:17-19,
+  CUDA implementation registered at :28-31, fake (meta) kernel of
+  /root/reference/codetr/ops.py:19-87.  Registered below from Python with the same
+  schema; the CUDA implementation calls the C ABI ``msda_b200_forward``
+  (include/msda_b200.h) through ctypes on torch's current stream.
+* ``DeformableAttentionPlugin::enqueue`` (TensorRT, raw device pointers, external
+  stream, device-resident int64 shapes,
+  /root/reference/codetr/csrc/deformable_attention_plugin.cpp:285-355)
+  -- :func:`plugin_enqueue` drives ``msda_b200_plugin_enqueue`` exactly that way.
+
+There is no CPU implementation and no fallback: CPU tensors hit the dispatcher's
+"no kernel for backend CPU" error exactly as they do with the reference's library
+(only the CUDA key is registered there too), and a missing ``libmsda_b200.so``
+raises at import of this module.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence
+
+import torch
+from torch import Tensor
+
+from . import _native
+
+_lib = _native.load()
+
+OP_SCHEMA = (
+    "multi_scale_deformable_attention(Tensor value, Tensor spatial_shapes, "
+    "Tensor level_start_index, Tensor sampling_loc, Tensor attn_weight, "
+    "int im2col_step) -> Tensor"
+)
+
+_DTYPES = {
+    torch.float32: _native.DTYPE_F32,
+    torch.float16: _native.DTYPE_F16,
+    torch.bfloat16: _native.DTYPE_BF16,
+    torch.float64: _native.DTYPE_F64,
+}
+# nvinfer1::DataType integer values used by the plugin path
+TRT_FLOAT, TRT_HALF, TRT_BF16 = 0, 1, 7
+_TRT_DTYPES = {torch.float32: TRT_FLOAT, torch.float16: TRT_HALF, torch.bfloat16: TRT_BF16}
+
+_default_flags = 0
+
+
+def set_default_flags(flags: int) -> int:
+    """Launch flags (``_native.FLAG_*``) applied by the registered torch op."""
+    global _default_flags
+    old, _default_flags = _default_flags, int(flags)
+    return old
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise RuntimeError(f"msda_b200 call failed ({rc}): {_native.error_string(rc)}")
+
+
+def _require(cond: bool, msg: str) -> None:
+    # the reference raises c10::Error (a RuntimeError in Python) from AT_ASSERTM
+    if not cond:
+        raise RuntimeError(msg)
+
+
+def _validate(value, spatial_shapes, level_start_index, sampling_loc, attn_weight) -> None:
+    # contiguity and device requirements of ms_deform_attn.cu:902-912
+    names = ("value", "spatial_shapes", "level_start_index", "sampling_loc", "attn_weight")
+    for name, t in zip(names, (value, spatial_shapes, level_start_index, sampling_loc, attn_weight)):
+        _require(t.is_contiguous(), f"{name} tensor has to be contiguous")
+        _require(t.is_cuda, f"{name} must be a CUDA tensor")
+        _require(t.device == value.device, f"{name} must be on the same device as value")
+    # rank / dtype / extent agreement of the reference's fake kernel, ops.py:59-84
+    _require(value.dim() == 4, "value must be [bs, num_keys, num_heads, dim_per_head]")
+    _require(spatial_shapes.dim() == 2 and spatial_shapes.shape[1] == 2, "spatial_shapes must be [num_levels, 2]")
+    _require(level_start_index.dim() == 1, "level_start_index must be [num_levels]")
+    _require(sampling_loc.dim() == 6, "sampling_loc must be [bs, num_queries, num_heads, num_levels, num_points, 2]")
+    _require(attn_weight.dim() == 5, "attn_weight must be [bs, num_queries, num_heads, num_levels, num_points]")
+    _require(value.dtype in _DTYPES, f"unsupported dtype {value.dtype}")
+    _require(value.dtype == sampling_loc.dtype == attn_weight.dtype, "value, sampling_loc, attn_weight dtypes differ")
+    _require(spatial_shapes.dtype == torch.int64, "spatial_shapes must be int64")
+    _require(level_start_index.dtype == torch.int64, "level_start_index must be int64")
+    bs, _, heads, _ = value.shape
+    levels = spatial_shapes.shape[0]
+    _require(level_start_index.shape[0] == levels, "level_start_index / spatial_shapes level count differ")
+    _require(
+        sampling_loc.shape[0] == bs and sampling_loc.shape[2] == heads and sampling_loc.shape[3] == levels
+        and sampling_loc.shape[5] == 2,
+        "sampling_loc shape does not match value / spatial_shapes",
+    )
+    _require(tuple(attn_weight.shape) == tuple(sampling_loc.shape[:5]), "attn_weight shape does not match sampling_loc")
+
+
+def _stream_ptr(device: torch.device, stream: Optional[int]) -> int:
+    return int(stream) if stream is not None else int(torch.cuda.current_stream(device).cuda_stream)
+
+
+def forward_into(
+    value: Tensor,
+    spatial_shapes: Tensor,
+    level_start_index: Tensor,
+    sampling_loc: Tensor,
+    attn_weight: Tensor,
+    output: Tensor,
+    im2col_step: int = 64,
+    flags: Optional[int] = None,
+    stream: Optional[int] = None,
+) -> Tensor:
+    """``codetr::ms_deform_attn_forward_reference`` (ms_deform_attn.cu:899-956): caller-owned output."""
+    _validate(value, spatial_shapes, level_start_index, sampling_loc, attn_weight)
+    bs, keys, heads, chans = value.shape
+    queries, levels, points = sampling_loc.shape[1], sampling_loc.shape[3], sampling_loc.shape[4]
+    _require(output.is_contiguous() and output.is_cuda, "output tensor has to be a contiguous CUDA tensor")
+    _require(tuple(output.shape) == (bs, queries, heads * chans), "output must be [bs, num_queries, num_heads*channels]")
+    _require(output.dtype == value.dtype and output.device == value.device, "output dtype/device must match value")
+    dev = value.device
+    guard = torch.cuda.device(dev) if torch.cuda.current_device() != dev.index else None
+    if guard is not None:
+        guard.__enter__()
+    try:
+        rc = _lib.msda_b200_forward(
+            value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), sampling_loc.data_ptr(),
+            attn_weight.data_ptr(), output.data_ptr(), bs, keys, heads, chans, levels, queries, points,
+            int(im2col_step), _DTYPES[value.dtype], _default_flags if flags is None else int(flags),
+            _stream_ptr(dev, stream),
+        )
+    finally:
+        if guard is not None:
+            guard.__exit__(None, None, None)
+    _check(rc)
+    return output
+
+
+def multi_scale_deformable_attention(
+    value: Tensor,
+    spatial_shapes: Tensor,
+    level_start_index: Tensor,
+    sampling_loc: Tensor,
+    attn_weight: Tensor,
+    im2col_step: int = 64,
+    flags: Optional[int] = None,
+) -> Tensor:
+    """``codetr::ms_deform_attn_forward`` (ms_deform_attn.cu:958-973): allocates ``[bs, num_queries, M*D]``."""
+    _validate(value, spatial_shapes, level_start_index, sampling_loc, attn_weight)
+    bs, _, heads, chans = value.shape
+    out = torch.empty((bs, sampling_loc.shape[1], heads * chans), dtype=value.dtype, device=value.device)
+    return forward_into(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, out, im2col_step, flags)
+
+
+def forward_fused(
+    value: Tensor,
+    spatial_shapes: Tensor,
+    level_start_index: Tensor,
+    reference_points: Tensor,
+    sampling_offsets: Tensor,
+    attn_logits: Tensor,
+    flags: Optional[int] = None,
+) -> Tensor:
+    """Opt-in producer-fused mode: softmax over L*P and the sampling-location arithmetic of
+    /root/reference/codetr/multi_scale_deformable_attention.py:180-200 happen inside the kernel.
+
+    ``reference_points [bs, Q, L, 2|4]``, ``sampling_offsets [bs, Q, M, L, P, 2]``,
+    ``attn_logits [bs, Q, M, L*P]`` (or ``[bs, Q, M, L, P]``)."""
+    for name, t in (("value", value), ("reference_points", reference_points), ("sampling_offsets", sampling_offsets),
+                    ("attn_logits", attn_logits), ("spatial_shapes", spatial_shapes),
+                    ("level_start_index", level_start_index)):
+        _require(t.is_contiguous(), f"{name} tensor has to be contiguous")
+        _require(t.is_cuda and t.device == value.device, f"{name} must be a CUDA tensor on value's device")
+    _require(value.dim() == 4 and sampling_offsets.dim() == 6 and reference_points.dim() == 4, "bad ranks")
+    _require(value.dtype in _DTYPES, f"unsupported dtype {value.dtype}")
+    _require(value.dtype == reference_points.dtype == sampling_offsets.dtype == attn_logits.dtype, "dtypes differ")
+    _require(spatial_shapes.dtype == torch.int64 and level_start_index.dtype == torch.int64, "shapes must be int64")
+    bs, keys, heads, chans = value.shape
+    _, queries, _, levels, points, _ = sampling_offsets.shape
+    ref_dim = reference_points.shape[-1]
+    _require(ref_dim in (2, 4), f"Last dim of reference_points must be 2 or 4, but get {ref_dim} instead.")
+    _require(tuple(reference_points.shape) == (bs, queries, levels, ref_dim), "reference_points shape mismatch")
+    _require(tuple(sampling_offsets.shape) == (bs, queries, heads, levels, points, 2), "sampling_offsets shape mismatch")
+    _require(attn_logits.numel() == bs * queries * heads * levels * points, "attn_logits shape mismatch")
+    out = torch.empty((bs, queries, heads * chans), dtype=value.dtype, device=value.device)
+    with torch.cuda.device(value.device):
+        rc = _lib.msda_b200_forward_fused(
+            value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), reference_points.data_ptr(),
+            sampling_offsets.data_ptr(), attn_logits.data_ptr(), out.data_ptr(), bs, keys, heads, chans, levels,
+            queries, points, ref_dim, _DTYPES[value.dtype], _default_flags if flags is None else int(flags),
+            _stream_ptr(value.device, None),
+        )
+    _check(rc)
+    return out
+
+
+def plugin_enqueue(
+    value_dims: Sequence[int],
+    loc_dims: Sequence[int],
+    trt_dtype: int,
+    input_ptrs: Sequence[int],
+    output_ptr: int,
+    stream: int,
+    im2col_step: int = 64,
+) -> int:
+    """Drive the library the way TensorRT drives ``DeformableAttentionPlugin::enqueue``
+    (deformable_attention_plugin.cpp:285-355): dims from the tensor descriptors, five raw
+    device pointers, one raw output pointer, an external ``cudaStream_t``.  Returns the
+    plugin's status code (0 = success) instead of raising, like ``enqueue``."""
+    vd = (ctypes.c_int64 * 4)(*[int(v) for v in value_dims])
+    ld = (ctypes.c_int64 * 6)(*[int(v) for v in loc_dims])
+    ins = (ctypes.c_void_p * 5)(*[int(p) for p in input_ptrs])
+    outs = (ctypes.c_void_p * 1)(int(output_ptr))
+    return int(_lib.msda_b200_plugin_enqueue(vd, ld, int(trt_dtype), ins, outs, None, int(im2col_step), int(stream)))
+
+
+class HostForward:
+    """End-to-end call for HOST buffers (``msda_b200_forward_host``): pinned inputs are copied
+    host->device into a reusable device workspace, the kernel runs, the result is copied back to a
+    pinned output -- all on one stream.  This is what ``bench.py`` times as ``e2e``."""
+
+    def __init__(self, device: torch.device):
+        self.device = torch.device(device)
+        self._ws: Optional[Tensor] = None
+
+    def __call__(self, value: Tensor, spatial_shapes: Tensor, level_start_index: Tensor, sampling_loc: Tensor,
+                 attn_weight: Tensor, output: Optional[Tensor] = None, im2col_step: int = 64,
+                 flags: Optional[int] = None, synchronize: bool = True) -> Tensor:
+        for t in (value, spatial_shapes, level_start_index, sampling_loc, attn_weight):
+            _require(not t.is_cuda and t.is_contiguous(), "HostForward takes contiguous host tensors")
+        bs, keys, heads, chans = value.shape
+        queries, levels, points = sampling_loc.shape[1], sampling_loc.shape[3], sampling_loc.shape[4]
+        dt = _DTYPES[value.dtype]
+        need = int(_lib.msda_b200_host_workspace_bytes(bs, keys, heads, chans, levels, queries, points, dt))
+        with torch.cuda.device(self.device):
+            if self._ws is None or self._ws.numel() < need:
+                self._ws = torch.empty(max(need, 256), dtype=torch.uint8, device=self.device)
+            if output is None:
+                output = torch.empty((bs, queries, heads * chans), dtype=value.dtype).pin_memory()
+            stream = torch.cuda.current_stream(self.device)
+            rc = _lib.msda_b200_forward_host(
+                value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), sampling_loc.data_ptr(),
+                attn_weight.data_ptr(), output.data_ptr(), self._ws.data_ptr(), self._ws.numel(), bs, keys, heads,
+                chans, levels, queries, points, int(im2col_step), dt,
+                _default_flags if flags is None else int(flags), int(stream.cuda_stream),
+            )
+            _check(rc)
+            if synchronize:
+                stream.synchronize()
+        return output
+
+    @staticmethod
+    def bytes_moved(value: Tensor, spatial_shapes: Tensor, level_start_index: Tensor, sampling_loc: Tensor,
+                    attn_weight: Tensor) -> tuple:
+        h2d = sum(t.numel() * t.element_size() for t in (value, spatial_shapes, level_start_index, sampling_loc, attn_weight))
+        d2h = value.shape[0] * sampling_loc.shape[1] * value.shape[2] * value.shape[3] * value.element_size()
+        return int(h2d), int(d2h)
+
+
+# ---------------------------------------------------------------------------
+# torch.library registration: same namespace, name and schema as the reference
+# ---------------------------------------------------------------------------
+def _fake(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step):
+    # output properties of the reference's fake kernel (ops.py:59-87)
+    torch._check(value.dim() == 4)
+    torch._check(spatial_shapes.dim() == 2)
+    torch._check(level_start_index.dim() == 1)
+    torch._check(sampling_loc.dim() == 6)
+    torch._check(attn_weight.dim() == 5)
+    torch._check(value.dtype == attn_weight.dtype)
+    torch._check(value.dtype == sampling_loc.dtype)
+    torch._check(spatial_shapes.dtype == torch.int64)
+    torch._check(level_start_index.dtype == torch.int64)
+    levels = spatial_shapes.shape[0]
+    torch._check(spatial_shapes.shape[1] == 2)
+    torch._check(level_start_index.shape[0] == levels)
+    torch._check(sampling_loc.shape[0] == value.shape[0])
+    torch._check(sampling_loc.shape[2] == value.shape[2])
+    torch._check(sampling_loc.shape[3] == levels)
+    torch._check(sampling_loc.shape[5] == 2)
+    for axis in range(5):
+        torch._check(attn_weight.shape[axis] == sampling_loc.shape[axis])
+    return value.new_empty((value.shape[0], sampling_loc.shape[1], value.shape[2] * value.shape[3]))
+
+
+def _op_cuda(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step):
+    return multi_scale_deformable_attention(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
+                                            im2col_step)
+
+
+_torch_lib = None
+
+
+def register_torch_op() -> None:
+    """Define ``codetr::multi_scale_deformable_attention`` unless a library that already defines it
+    (the reference's own ``codetr_cpp_extension.so``, or our ATen adapter build) is loaded."""
+    global _torch_lib
+    if _torch_lib is not None:
+        return
+    already = hasattr(torch.ops, "codetr") and hasattr(torch.ops.codetr, "multi_scale_deformable_attention")
+    if already:
+        _torch_lib = False
+        return
+    lib = torch.library.Library("codetr", "DEF")
+    lib.define(OP_SCHEMA)
+    lib.impl("multi_scale_deformable_attention", _op_cuda, "CUDA")
+    torch.library.register_fake("codetr::multi_scale_deformable_attention", _fake, lib=lib)
+    _torch_lib = lib
+
+
+register_torch_op()

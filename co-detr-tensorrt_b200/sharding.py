@@ -1,0 +1,49 @@
+"""Batch sharding for the multi-GPU path.
+
+The op has no cross-image term (the kernel index decomposes into an image index first,
+/root/reference/codetr/csrc/ms_deform_attn.cu:226-232), so a batch shards by image with no
+data-path collective: rank r of N owns a contiguous block of images.  The only communication is
+the timing/accounting reduction done by the caller (``bench.py``) after the work.
+"""
+from __future__ import annotations
+
+from typing import List, Tuple
+
+
+def image_range(num_images: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """Half-open range of images owned by ``rank``: contiguous blocks, sizes differ by at most one,
+    lower ranks take the remainder."""
+    if world_size <= 0 or not (0 <= rank < world_size):
+        raise ValueError(f"bad rank/world_size {rank}/{world_size}")
+    if num_images < 0:
+        raise ValueError("num_images must be >= 0")
+    base, extra = divmod(num_images, world_size)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def all_ranges(num_images: int, world_size: int) -> List[Tuple[int, int]]:
+    return [image_range(num_images, r, world_size) for r in range(world_size)]
+
+
+def shard_batch(tensors, rank: int, world_size: int):
+    """Slice every batched tensor (dim 0 = image) to this rank's images; tensors without a batch
+    dimension (``spatial_shapes``, ``level_start_index``) are replicated, i.e. passed as None -> None
+    or returned unchanged when marked with ``replicate=True`` via a (tensor, True) tuple."""
+    out = []
+    for item in tensors:
+        if isinstance(item, tuple):
+            t, replicate = item
+        else:
+            t, replicate = item, False
+        if t is None or replicate:
+            out.append(t)
+            continue
+        lo, hi = image_range(t.shape[0], rank, world_size)
+        out.append(t[lo:hi])
+    return out
+
+
+def weak_scaling_images(per_gpu_batch: int, world_size: int) -> int:
+    """Weak scaling: per-GPU work is fixed, the job's image count grows with the GPU count."""
+    return per_gpu_batch * world_size

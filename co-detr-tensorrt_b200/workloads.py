@@ -1,0 +1,231 @@
+"""Co-DINO shaped synthetic workloads for the MSDA forward path.
+
+Everything here is deterministic numpy (``np.random.default_rng``, PCG64), so the same
+arrays can be regenerated in the build container (golden fixtures), in the tests and on
+the GPU box.  Shapes follow the reference's model: embed 256 = 8 heads x 32 channels,
+4 points, 5 levels (configs/co_dino_5scale_swin_l_16xb1_16e_o365tococo.py), levels
+``ceil(H_img / stride)`` x ``ceil(W_img / stride)``.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+STRIDES_BASELINE = (8, 16, 32, 64, 128)   # BASELINE.json ("5 levels at strides 8-128"), the judged shapes
+STRIDES_REFERENCE = (4, 8, 16, 32, 64)    # what the reference's model really runs (tests/test_export.py:238)
+
+
+def pyramid_shapes(img_h: int, img_w: int, strides: Sequence[int] = STRIDES_BASELINE) -> List[Tuple[int, int]]:
+    """(H_l, W_l) per level for an image of ``img_h x img_w`` pixels."""
+    return [(math.ceil(img_h / s), math.ceil(img_w / s)) for s in strides]
+
+
+def level_starts(shapes: Sequence[Tuple[int, int]]) -> List[int]:
+    out, acc = [], 0
+    for h, w in shapes:
+        out.append(acc)
+        acc += h * w
+    return out
+
+
+def num_keys(shapes: Sequence[Tuple[int, int]]) -> int:
+    return sum(h * w for h, w in shapes)
+
+
+@dataclass(frozen=True)
+class Workload:
+    """One named configuration of the op."""
+    name: str
+    shapes: Tuple[Tuple[int, int], ...]
+    num_queries: int          # 0 -> encoder self-attention, Q = S
+    batch: int = 1
+    num_heads: int = 8
+    channels: int = 32
+    num_points: int = 4
+    kind: str = "encoder"     # "encoder" | "decoder" | "uniform"
+    dtype: str = "float16"
+    seed: int = 1234
+    note: str = ""
+
+    @property
+    def S(self) -> int:
+        return num_keys(self.shapes)
+
+    @property
+    def Q(self) -> int:
+        return self.num_queries if self.num_queries > 0 else self.S
+
+    @property
+    def L(self) -> int:
+        return len(self.shapes)
+
+    def dims(self) -> Dict[str, int]:
+        return dict(B=self.batch, S=self.S, M=self.num_heads, D=self.channels, L=self.L, Q=self.Q, P=self.num_points)
+
+    def with_(self, **kw) -> "Workload":
+        d = dict(self.__dict__)
+        d.update(kw)
+        return Workload(**d)
+
+
+def _enc(name, h, w, strides, **kw) -> Workload:
+    return Workload(name=name, shapes=tuple(pyramid_shapes(h, w, strides)), num_queries=0, kind="encoder", **kw)
+
+
+def _dec(name, h, w, strides, q, **kw) -> Workload:
+    return Workload(name=name, shapes=tuple(pyramid_shapes(h, w, strides)), num_queries=q, kind="decoder", **kw)
+
+
+# BASELINE.json `configs`, in order.  configs[0] is the reference's CPU-runnable test shape
+# (tests/test_multi_scale_deformable_attention.py:423-428); the rest are Co-DINO shapes.
+CONFIGS: Dict[str, Workload] = {
+    "ref_test_mid_fp32": Workload(
+        name="ref_test_mid_fp32", shapes=((64, 64), (32, 32), (16, 16), (8, 8)), num_queries=100, num_heads=8,
+        channels=64, num_points=4, kind="uniform", dtype="float32", seed=1234,
+        note="configs[0]: reference test_benchmark_performance shape, fp32, bs=1"),
+    "r50_enc_608": _enc("r50_enc_608", 608, 608, STRIDES_BASELINE, dtype="float16", seed=1235,
+                        note="configs[1]: Co-DINO R50 encoder self-attn at 608x608"),
+    "swinl_enc_1152x768": _enc("swinl_enc_1152x768", 768, 1152, STRIDES_BASELINE, dtype="float16", seed=1236,
+                               note="configs[2]: Co-DINO Swin-L encoder at 1152x768, S=Q=18,414 (headline)"),
+    "swinl_dec_1152x768": _dec("swinl_dec_1152x768", 768, 1152, STRIDES_BASELINE, 900, dtype="float16", seed=1237,
+                               note="configs[3]: decoder cross-attn, 900 queries over the 1152x768 pyramid"),
+    "swinl_enc_1920x1280": _enc("swinl_enc_1920x1280", 1280, 1920, STRIDES_BASELINE, batch=2, dtype="float16",
+                                seed=1238, note="configs[4]: Swin-L encoder at 1920x1280, S=Q=51,150, B=2 per GPU"),
+    # extra rows: the strides the reference's model really uses (SURVEY.md finding 1)
+    "swinl_enc_1152x768_s4": _enc("swinl_enc_1152x768_s4", 768, 1152, STRIDES_REFERENCE, dtype="float16", seed=1239,
+                                  note="extra: reference-true strides 4-64, S=Q=73,656"),
+    "swinl_dec_1900q": _dec("swinl_dec_1900q", 768, 1152, STRIDES_BASELINE, 1900, dtype="float16", seed=1240,
+                            note="extra: decoder with 900 + 2x500 denoising queries"),
+}
+
+HEADLINE = "swinl_enc_1152x768"
+
+
+@dataclass
+class Inputs:
+    """Host (numpy) tensors of one call, in the op's layouts."""
+    value: np.ndarray              # [B,S,M,D]
+    spatial_shapes: np.ndarray     # [L,2] int64 (H,W)
+    level_start_index: np.ndarray  # [L] int64
+    sampling_loc: np.ndarray       # [B,Q,M,L,P,2]
+    attn_weight: np.ndarray        # [B,Q,M,L,P]
+    # producers of loc / weight, for the fused entry point (None when not generated)
+    reference_points: Optional[np.ndarray] = None   # [B,Q,L,2|4]
+    sampling_offsets: Optional[np.ndarray] = None   # [B,Q,M,L,P,2]
+    attn_logits: Optional[np.ndarray] = None        # [B,Q,M,L,P]
+    meta: Dict[str, object] = field(default_factory=dict)
+
+
+def _head_directions(num_heads: int) -> np.ndarray:
+    """Initial offset direction of each head: unit L-inf vectors around the circle
+    (the module's bias init, codetr/multi_scale_deformable_attention.py:101-111)."""
+    th = np.arange(num_heads, dtype=np.float64) * (2.0 * math.pi / num_heads)
+    g = np.stack([np.cos(th), np.sin(th)], -1)
+    return g / np.abs(g).max(-1, keepdims=True)
+
+
+def _softmax(x: np.ndarray, axis: int) -> np.ndarray:
+    x = x - x.max(axis=axis, keepdims=True)
+    e = np.exp(x)
+    return e / e.sum(axis=axis, keepdims=True)
+
+
+def make_inputs(
+    wl: Workload,
+    batch: Optional[int] = None,
+    seed: Optional[int] = None,
+    loc_mode: Optional[str] = None,
+    out_of_range_frac: float = 0.0,
+    pad_frac: float = 0.10,
+    dtype: np.dtype = np.float32,
+) -> Inputs:
+    """Synthetic inputs for ``wl``.
+
+    ``loc_mode``: "encoder" (reference point = the query's own pixel centre, offsets of a few
+    pixels along the head's direction, transformer.py:280-305 + module init), "decoder"
+    (reference boxes, ``cxcy + off/P * wh/2``), or "uniform" (``rand`` in [0,1), what the
+    reference's tests use -- worst case for locality).  ``out_of_range_frac`` pushes that share of
+    locations outside [0,1] (boundary parity).  ``pad_frac`` zeroes a right/bottom band of keys, like
+    ``masked_fill(key_padding_mask)`` (multi_scale_deformable_attention.py:174-175).
+    """
+    B = wl.batch if batch is None else int(batch)
+    rng = np.random.default_rng(wl.seed if seed is None else seed)
+    mode = loc_mode or wl.kind
+    M, D, P, L, S, Q = wl.num_heads, wl.channels, wl.num_points, wl.L, wl.S, wl.Q
+    shapes = np.asarray(wl.shapes, dtype=np.int64).reshape(L, 2)
+    starts = np.asarray(level_starts(wl.shapes), dtype=np.int64)
+
+    value = rng.standard_normal((B, S, M, D), dtype=np.float32)
+    if pad_frac > 0:
+        for b in range(B):
+            keep_h, keep_w = 1.0 - pad_frac * rng.random(), 1.0 - pad_frac * rng.random()
+            for (h, w), st in zip(wl.shapes, starts):
+                lvl = value[b, st:st + h * w].reshape(h, w, M, D)
+                lvl[int(math.ceil(h * keep_h)):, :] = 0
+                lvl[:, int(math.ceil(w * keep_w)):] = 0
+
+    logits = rng.standard_normal((B, Q, M, L, P), dtype=np.float32)
+    weight = _softmax(logits.reshape(B, Q, M, L * P).astype(np.float64), -1).reshape(B, Q, M, L, P).astype(np.float32)
+
+    wh = np.stack([shapes[:, 1], shapes[:, 0]], -1).astype(np.float32)  # (W,H) per level
+    ref = offsets = None
+    if mode == "uniform":
+        loc = rng.random((B, Q, M, L, P, 2), dtype=np.float32)
+    else:
+        dirs = _head_directions(M).astype(np.float32)                     # [M,2]
+        scale = (np.arange(P, dtype=np.float32) + 1.0)                    # point p sits (p+1) steps out
+        offsets = dirs[None, None, :, None, None, :] * scale[None, None, None, None, :, None]
+        offsets = offsets + 1.5 * rng.standard_normal((B, Q, M, L, P, 2), dtype=np.float32)
+        offsets = offsets.astype(np.float32)
+        if mode == "encoder":
+            assert Q == S, "encoder workloads have one query per key"
+            centres = []
+            for h, w in wl.shapes:
+                ys, xs = np.meshgrid((np.arange(h, dtype=np.float32) + 0.5) / h,
+                                     (np.arange(w, dtype=np.float32) + 0.5) / w, indexing="ij")
+                centres.append(np.stack([xs.reshape(-1), ys.reshape(-1)], -1))
+            centre = np.concatenate(centres, 0)                            # [Q,2] (x,y)
+            ref = np.broadcast_to(centre[None, :, None, :], (B, Q, L, 2)).astype(np.float32).copy()
+            loc = ref[:, :, None, :, None, :] + offsets / wh[None, None, None, :, None, :]
+        elif mode == "decoder":
+            cxcy = rng.random((B, Q, 1, 2), dtype=np.float32)
+            box = 0.02 + 0.48 * rng.random((B, Q, 1, 2), dtype=np.float32)
+            ref = np.broadcast_to(np.concatenate([cxcy, box], -1), (B, Q, L, 4)).astype(np.float32).copy()
+            loc = ref[:, :, None, :, None, :2] + offsets / np.float32(P) * ref[:, :, None, :, None, 2:] * np.float32(0.5)
+        else:
+            raise ValueError(f"unknown loc_mode {mode!r}")
+        loc = loc.astype(np.float32)
+
+    if out_of_range_frac > 0:
+        mask = rng.random((B, Q, M, L, P)) < out_of_range_frac
+        far = rng.uniform(-0.5, 1.5, size=(B, Q, M, L, P, 2)).astype(np.float32)
+        loc = np.where(mask[..., None], far, loc)
+        ref = offsets = None  # producers no longer describe loc
+
+    inp = Inputs(
+        value=value.astype(dtype, copy=False), spatial_shapes=shapes, level_start_index=starts,
+        sampling_loc=np.ascontiguousarray(loc.astype(dtype, copy=False)),
+        attn_weight=np.ascontiguousarray(weight.astype(dtype, copy=False)),
+        reference_points=None if ref is None else np.ascontiguousarray(ref.astype(dtype, copy=False)),
+        sampling_offsets=None if offsets is None else np.ascontiguousarray(offsets.astype(dtype, copy=False)),
+        attn_logits=None if offsets is None else np.ascontiguousarray(logits.astype(dtype, copy=False)),
+        meta=dict(workload=wl.name, batch=B, loc_mode=mode, out_of_range_frac=out_of_range_frac, pad_frac=pad_frac),
+    )
+    return inp
+
+
+def algorithmic_hbm_bytes(wl: Workload, batch: int, elem_size: int) -> int:
+    """Compulsory HBM traffic of one call: every input read once, output written once
+    (SURVEY.md section 8(d)): E*B*(S*M*D + 3*Q*M*L*P + Q*M*D) + 24*L."""
+    d = wl.dims()
+    return elem_size * batch * (d["S"] * d["M"] * d["D"] + 3 * d["Q"] * d["M"] * d["L"] * d["P"]
+                                + d["Q"] * d["M"] * d["D"]) + 24 * d["L"]
+
+
+def algorithmic_gather_bytes(wl: Workload, batch: int, elem_size: int) -> int:
+    """No-reuse gather volume: B*Q*M*L*P*4 corner rows of D elements."""
+    d = wl.dims()
+    return elem_size * batch * d["Q"] * d["M"] * d["L"] * d["P"] * 4 * d["D"]

@@ -1,0 +1,184 @@
+/*
+ * msda_b200.h -- C ABI of the B200-native (sm_100a) multi-scale deformable
+ * attention forward core.
+ *
+ * This is the drop-in boundary of the repo: a plain-C shared library
+ * (libmsda_b200.so) with no torch / ATen / TensorRT types in its signatures.
+ * Every entry point below names the reference interface it stands behind
+ * (citations are file:line under the reference checkout, anenbergb/Co-DETR-TensorRT).
+ *
+ * Conventions shared by all launch entry points
+ *   - all data pointers are DEVICE pointers unless the name says "_host";
+ *   - tensors are dense row-major ("contiguous" in the reference's asserts,
+ *     codetr/csrc/ms_deform_attn.cu:902-912):
+ *         value              [B, S, M, D]          element type = dtype
+ *         spatial_shapes     [L, 2]  int64, (H, W) per level          (device)
+ *         level_start_index  [L]     int64, first key of each level   (device)
+ *         sampling_loc       [B, Q, M, L, P, 2]    (x, y) in [0,1] units
+ *         attn_weight        [B, Q, M, L, P]       already soft-maxed
+ *         output             [B, Q, M*D]           fully overwritten
+ *   - the launcher never allocates, never synchronises, never reads device
+ *     memory on the host, and enqueues work only on `stream` (a cudaStream_t
+ *     passed as void*; NULL = legacy default stream).  It is therefore safe
+ *     under CUDA-graph capture and re-entrant from several host threads, which
+ *     is what TensorRT's enqueue contract needs
+ *     (codetr/csrc/deformable_attention_plugin.cpp:285-355, README.md:193);
+ *   - `output` does not have to be zeroed by the caller (the reference zero
+ *     fills twice, ms_deform_attn.cu:936 and :968, then overwrites);
+ *   - return value: 0 on success, a negative MSDA_ERR_* for a rejected call,
+ *     or a positive cudaError_t if the launch itself failed (the reference
+ *     only printf()s launch errors, ms_deform_attn.cu:775-778).
+ */
+#ifndef MSDA_B200_H_
+#define MSDA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSDA_B200_ABI_VERSION 1
+
+/* Element type of value / sampling_loc / attn_weight / output.  The reference
+ * dispatches double, float and half (AT_DISPATCH_FLOATING_TYPES_AND_HALF,
+ * ms_deform_attn.cu:946); bf16 is new here. */
+enum msda_dtype {
+  MSDA_F32 = 0,
+  MSDA_F16 = 1,
+  MSDA_BF16 = 2,
+  MSDA_F64 = 3
+};
+
+enum msda_error {
+  MSDA_OK = 0,
+  MSDA_ERR_NULL_POINTER = -1,   /* a required pointer is NULL                         */
+  MSDA_ERR_BAD_SHAPE = -2,      /* a dimension is negative / zero where not allowed   */
+  MSDA_ERR_BAD_DTYPE = -3,      /* dtype is not one of msda_dtype                     */
+  MSDA_ERR_BAD_STEP = -4,       /* B % min(B, im2col_step) != 0 (ms_deform_attn.cu:924-926) */
+  MSDA_ERR_MISALIGNED = -5,     /* a pointer is not aligned to its element size       */
+  MSDA_ERR_UNSUPPORTED = -6,    /* shape outside what the kernels index (e.g. > 2^31 keys) */
+  MSDA_ERR_BAD_FLAGS = -7
+};
+
+/* Launch flags (bit field).  0 = library defaults. */
+enum msda_flags {
+  MSDA_FLAG_DEFAULT = 0,
+  MSDA_FLAG_FORCE_GENERIC = 1 << 0, /* use the shape-agnostic scalar kernel               */
+  MSDA_FLAG_LINEAR_ORDER = 1 << 1,  /* do not re-tile queries spatially (encoder shapes)  */
+  MSDA_FLAG_MATH_FHFMA = 1 << 2,    /* fp16/bf16: Blackwell FHFMA with 16-bit weights     */
+  MSDA_FLAG_MATH_EXACT = 1 << 3,    /* fp16/bf16: fp32 weights, convert + FFMA            */
+  MSDA_FLAG_NO_STAGING = 1 << 4     /* do not stage loc/weights through shared memory     */
+};
+
+/*
+ * msda_b200_forward -- the forward core.
+ *
+ * Stands behind  codetr::ms_deform_attn_forward_reference
+ *   (codetr/csrc/ms_deform_attn.cu:899-956; declared extern by the TensorRT
+ *   plugin, codetr/csrc/deformable_attention_plugin.cpp:64-69, called :351)
+ * and, with a caller-allocated output, behind  codetr::ms_deform_attn_forward
+ *   (ms_deform_attn.cu:958-973; bound to the torch op
+ *   codetr::multi_scale_deformable_attention in
+ *   codetr/csrc/deformable_attention_torch.cpp:17-19, :28-31).
+ *
+ * im2col_step keeps the reference's argument: it must satisfy
+ * B % min(B, im2col_step) == 0, otherwise MSDA_ERR_BAD_STEP.  It does not
+ * change the result and (unlike the reference, which launches once per chunk)
+ * does not change the number of launches: one kernel covers the whole batch.
+ */
+int msda_b200_forward(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                      const void *sampling_loc, const void *attn_weight, void *output, int64_t batch,
+                      int64_t num_keys, int64_t num_heads, int64_t channels, int64_t num_levels,
+                      int64_t num_queries, int64_t num_points, int64_t im2col_step, int dtype,
+                      unsigned flags, void *stream);
+
+/*
+ * msda_b200_plugin_enqueue -- the TensorRT IPluginV3OneRuntime::enqueue body
+ * without libtorch.
+ *
+ * Stands behind  DeformableAttentionPlugin::enqueue
+ *   (codetr/csrc/deformable_attention_plugin.cpp:285-355): `inputs` is the
+ *   plugin's five device pointers in the plugin's order {value,
+ *   spatial_shapes, level_start_index, sampling_loc, attn_weight}, `outputs[0]`
+ *   the output buffer; value_dims = inputDesc[0].dims.d (4 entries),
+ *   loc_dims = inputDesc[3].dims.d (6 entries); trt_dtype is the integer value
+ *   of nvinfer1::DataType of input 0 (kFLOAT = 0, kHALF = 1, kBF16 = 7).
+ * Returns 0 on success and non-zero on failure, like enqueue (:320-325).
+ */
+int msda_b200_plugin_enqueue(const int64_t *value_dims, const int64_t *loc_dims, int trt_dtype,
+                             const void *const *inputs, void *const *outputs, void *workspace,
+                             int64_t im2col_step, void *stream);
+
+/*
+ * msda_b200_forward_fused -- opt-in producer-fused mode (not part of the
+ * reference's operator API).
+ *
+ * Replaces, for callers that opt in, the softmax over L*P and the sampling
+ * location arithmetic that the reference module performs before calling the
+ * op (codetr/multi_scale_deformable_attention.py:180-200), so the [B,Q,M,L,P]
+ * weights and [B,Q,M,L,P,2] locations never round-trip through HBM:
+ *     attn_logits      [B, Q, M, L*P]     pre-softmax
+ *     sampling_offsets [B, Q, M, L, P, 2] raw Linear output
+ *     reference_points [B, Q, L, ref_dim] ref_dim = 2 (x,y) or 4 (cx,cy,w,h)
+ */
+int msda_b200_forward_fused(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                            const void *reference_points, const void *sampling_offsets,
+                            const void *attn_logits, void *output, int64_t batch, int64_t num_keys,
+                            int64_t num_heads, int64_t channels, int64_t num_levels, int64_t num_queries,
+                            int64_t num_points, int64_t ref_dim, int dtype, unsigned flags, void *stream);
+
+/*
+ * msda_b200_forward_host -- the same call for HOST buffers: copies the five
+ * inputs host->device into a caller-provided device workspace, launches, and
+ * copies the output back, all on `stream` (asynchronous when the host buffers
+ * are pinned).  This is the end-to-end path a caller without device-resident
+ * tensors takes (what bench.py reports as "e2e").  workspace_bytes must be at
+ * least msda_b200_host_workspace_bytes(...).  The caller synchronises `stream`.
+ */
+size_t msda_b200_host_workspace_bytes(int64_t batch, int64_t num_keys, int64_t num_heads, int64_t channels,
+                                      int64_t num_levels, int64_t num_queries, int64_t num_points, int dtype);
+int msda_b200_forward_host(const void *value_host, const int64_t *spatial_shapes_host,
+                           const int64_t *level_start_index_host, const void *sampling_loc_host,
+                           const void *attn_weight_host, void *output_host, void *workspace_dev,
+                           size_t workspace_bytes, int64_t batch, int64_t num_keys, int64_t num_heads,
+                           int64_t channels, int64_t num_levels, int64_t num_queries, int64_t num_points,
+                           int64_t im2col_step, int dtype, unsigned flags, void *stream);
+
+/* ---- introspection / measurement helpers (no reference counterpart) ---- */
+
+/* ABI version of the loaded library (== MSDA_B200_ABI_VERSION). */
+int msda_b200_abi_version(void);
+
+/* Human-readable text for a return value of the functions above. */
+const char *msda_b200_error_string(int code);
+
+/* Number of kernels this library has launched in this process (all threads). */
+uint64_t msda_b200_launch_count(void);
+
+/* Name of the kernel variant the last successful msda_b200_forward* call on
+ * this host thread selected, e.g. "vec<f16,D32,P4>/tiled/exact". */
+const char *msda_b200_last_variant(void);
+
+/* Algorithmic byte counts of one forward call:
+ * compulsory HBM bytes (every input read once, output written once) and the
+ * no-reuse gather bytes (every corner row fetched separately). */
+uint64_t msda_b200_algorithmic_hbm_bytes(int64_t batch, int64_t num_keys, int64_t num_heads, int64_t channels,
+                                         int64_t num_levels, int64_t num_queries, int64_t num_points, int dtype);
+uint64_t msda_b200_algorithmic_gather_bytes(int64_t batch, int64_t num_heads, int64_t channels,
+                                            int64_t num_levels, int64_t num_queries, int64_t num_points,
+                                            int dtype);
+
+/* Read-bandwidth probe used for the roofline denominators that
+ * MEASURED_PEAKS.json does not carry (L2): every thread block streams
+ * `bytes` of `buf` (16-byte loads) `repeats` times; a working set below the
+ * L2 capacity measures L2->SM bandwidth, a larger one HBM.  `sink` receives a
+ * checksum so the loads cannot be elided (>= 4 bytes, device). */
+int msda_b200_read_probe(const void *buf, size_t bytes, int repeats, void *sink, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* MSDA_B200_H_ */
