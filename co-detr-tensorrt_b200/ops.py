@@ -152,6 +152,34 @@ def multi_scale_deformable_attention(
     return forward_into(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, out, im2col_step, flags)
 
 
+class PreparedForward:
+    """A validated, pointer-bound call (the analogue of a TensorRT execution context with its tensor
+    addresses set): arguments are checked once, each ``__call__`` is a single C-ABI call on the
+    given (default: torch's current) stream.  The tensors are kept alive by the object."""
+
+    def __init__(self, value: Tensor, spatial_shapes: Tensor, level_start_index: Tensor, sampling_loc: Tensor,
+                 attn_weight: Tensor, output: Optional[Tensor] = None, im2col_step: int = 64, flags: Optional[int] = None):
+        _validate(value, spatial_shapes, level_start_index, sampling_loc, attn_weight)
+        bs, keys, heads, chans = value.shape
+        queries, levels, points = sampling_loc.shape[1], sampling_loc.shape[3], sampling_loc.shape[4]
+        if output is None:
+            output = torch.empty((bs, queries, heads * chans), dtype=value.dtype, device=value.device)
+        _require(output.is_contiguous() and tuple(output.shape) == (bs, queries, heads * chans)
+                 and output.dtype == value.dtype and output.device == value.device, "bad output tensor")
+        self.tensors = (value, spatial_shapes, level_start_index, sampling_loc, attn_weight, output)
+        self.output = output
+        self.device = value.device
+        self._args = (value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), sampling_loc.data_ptr(),
+                      attn_weight.data_ptr(), output.data_ptr(), bs, keys, heads, chans, levels, queries, points,
+                      int(im2col_step), _DTYPES[value.dtype], _default_flags if flags is None else int(flags))
+
+    def __call__(self, stream: Optional[int] = None) -> Tensor:
+        rc = _lib.msda_b200_forward(*self._args, _stream_ptr(self.device, stream))
+        if rc != 0:
+            _check(rc)
+        return self.output
+
+
 def forward_fused(
     value: Tensor,
     spatial_shapes: Tensor,

@@ -1,0 +1,28 @@
+#!/bin/bash
+# One GPU-box session: parity tests, smoke, tuning sweep, bench line, ncu launch list + full capture.
+# Usage (from the build container):  gpurun --timeout 1800 -- bash tools/gpu_round.sh [stages...]
+# Everything is written under gpurun_out/ (merged back by gpurun).
+cd "${GRAFT_REPO_ROOT:-/root/repo}"
+mkdir -p gpurun_out
+STAGES="${@:-tests smoke sweep bench ncu}"
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > gpurun_out/nvidia_smi.csv 2>&1
+for st in $STAGES; do
+  case $st in
+    tests)
+      timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" | tee -a gpurun_out/pytest_gpu.log
+      tail -5 gpurun_out/pytest_gpu.log ;;
+    smoke)
+      timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke exit $?"; tail -5 gpurun_out/smoke.log ;;
+    sweep)
+      timeout 900 python tests/perf_sweep.py --out gpurun_out/sweep.json > gpurun_out/sweep.log 2>&1; echo "sweep exit $?"; tail -3 gpurun_out/sweep.log ;;
+    bench)
+      timeout 600 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $?"; cat gpurun_out/bench.json
+      timeout 300 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/bench_reference.json 2>> gpurun_out/bench.err; cat gpurun_out/bench_reference.json ;;
+    ncu)
+      timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches.csv \
+        python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1; echo "ncu launches exit $?"
+      timeout 600 ncu --set full --clock-control none --import-source on -k regex:msda_fwd -s 6 -c 2 -f -o gpurun_out/prof_headline \
+        python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_full.log 2>&1; echo "ncu full exit $?" ;;
+  esac
+done
+ls -la gpurun_out | tail -20
