@@ -19,7 +19,8 @@ _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 _REPO_ROOT = os.path.dirname(_PKG_DIR)
 CSRC_DIR = os.path.join(_PKG_DIR, "csrc")
 INCLUDE_DIR = os.path.join(_REPO_ROOT, "include")
-LIB_PATH = os.path.join(CSRC_DIR, "libmsda_b200.so")
+# MSDA_B200_LIB lets tuning experiments load an alternative build of the same sources
+LIB_PATH = os.environ.get("MSDA_B200_LIB") or os.path.join(CSRC_DIR, "libmsda_b200.so")
 SOURCES = [os.path.join(CSRC_DIR, "msda_sm100.cu")]
 HEADERS = [os.path.join(INCLUDE_DIR, "msda_b200.h")]
 
@@ -69,6 +70,8 @@ def _nvcc() -> str:
 
 
 def is_stale() -> bool:
+    if os.environ.get("MSDA_B200_LIB"):
+        return False
     if not os.path.isfile(LIB_PATH):
         return True
     built = os.path.getmtime(LIB_PATH)

@@ -56,6 +56,12 @@ namespace {
 
 constexpr int kMaxLevelsSmem = 16;  // levels cached in shared memory by the fast kernels
 constexpr int kThreads = 256;
+#ifndef MSDA_MINB
+#define MSDA_MINB 3
+#endif
+#ifndef MSDA_NB
+#define MSDA_NB 2
+#endif
 
 std::atomic<uint64_t> g_launch_count{0};
 thread_local char g_last_variant[128] = "none";
@@ -106,7 +112,9 @@ struct MsdaParams {
   void *out;              // [B,Q,M*D]
   int B, S, M, D, L, Q, P;
   int ref_dim;  // 0 = plain mode, 2 or 4 = fused mode
-  int tile_w, tile_h;   // query tile (tiled order) ; tile_w*tile_h queries per tile in linear order
+  int tile_w_log2, tile_h_log2;  // query tile is 2^tile_w_log2 x 2^tile_h_log2 (tiled) or that many consecutive queries (linear)
+  int passes;           // CTA passes per tile = ceil(tile queries * M / pairs per pass)
+  float inv_passes, inv_M;       // reciprocals for fast_div
   int want_tiled;       // 1: use 2-D tiles when sum(H*W) == Q
   int head_major;       // 1: a warp holds one head of 32/G neighbouring queries
 };
@@ -389,6 +397,66 @@ __device__ __forceinline__ void store_row<__nv_bfloat16, 8>(__nv_bfloat16 *dst, 
   *reinterpret_cast<uint4 *>(dst) = o;
 }
 
+// Lean sample geometry for the vector kernels.  Follows ms_deform_attn.cu:246-249 and :35-73 like
+// make_sample(), but folds every "does not contribute" case into a zero weight: a corner outside the
+// level, or a sample that fails the whole-sample range test (including NaN / infinite locations, for
+// which every comparison is false).  Selects, not multiplications, produce the zeros, so non-finite
+// intermediates never leak.  i00 is the pixel index of the top-left corner inside the level; it is only
+// meaningful for corners whose weight is non-zero.
+__device__ __forceinline__ void make_geo(float x, float y, float aw, int H, int W, int &i00, float (&cw)[4]) {
+  const float w_im = __fmul_rn(x, (float)W) - 0.5f;  // product rounded first, like the reference
+  const float h_im = __fmul_rn(y, (float)H) - 0.5f;
+  const bool inside = (h_im > -1.f) && (w_im > -1.f) && (h_im < (float)H) && (w_im < (float)W);
+  const float hf = floorf(h_im), wf = floorf(w_im);
+  const int h_lo = (int)hf, w_lo = (int)wf;
+  const float lh = h_im - hf, lw = w_im - wf;
+  const float hh = 1.f - lh, hw = 1.f - lw;
+  const float wy0 = (inside && h_lo >= 0) ? hh * aw : 0.f;
+  const float wy1 = (inside && h_lo < H - 1) ? lh * aw : 0.f;
+  const float wx0 = (inside && w_lo >= 0) ? hw : 0.f;
+  const float wx1 = (inside && w_lo < W - 1) ? lw : 0.f;
+  cw[0] = wy0 * wx0;
+  cw[1] = wy0 * wx1;
+  cw[2] = wy1 * wx0;
+  cw[3] = wy1 * wx1;
+  i00 = h_lo * W + w_lo;
+}
+
+// location (x, y) and attention weight of sample `si` of a (query, head) pair, as floats
+template <typename T>
+__device__ __forceinline__ void load_sample_inputs(const T *lp, const T *wp, int si, float &x, float &y, float &aw) {
+  if constexpr (sizeof(T) == 2) {
+    const float2 xy = unpack2<T>(__ldg(reinterpret_cast<const unsigned *>(lp) + si));
+    x = xy.x;
+    y = xy.y;
+    const unsigned short wraw = __ldg(reinterpret_cast<const unsigned short *>(wp) + si);
+    aw = unpack2<T>((unsigned)wraw).x;
+  } else {
+    const float2 xy = __ldg(reinterpret_cast<const float2 *>(lp) + si);
+    x = xy.x;
+    y = xy.y;
+    aw = __ldg(reinterpret_cast<const float *>(wp) + si);
+  }
+}
+
+// two fp32 weights -> packed 16-bit pair in the element type (low half = first)
+template <typename T>
+__device__ __forceinline__ unsigned pack_weights(float a, float b);
+template <>
+__device__ __forceinline__ unsigned pack_weights<__half>(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const unsigned *>(&h);
+}
+template <>
+__device__ __forceinline__ unsigned pack_weights<__nv_bfloat16>(float a, float b) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const unsigned *>(&h);
+}
+template <>
+__device__ __forceinline__ unsigned pack_weights<float>(float, float) {
+  return 0u;
+}
+
 // ---- TMA 1-D bulk copy + mbarrier (Blackwell/Hopper async proxy) ----
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -426,9 +494,28 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gme
 // ---------------------------------------------------------------------------
 // Tile bookkeeping shared by the vector kernels
 // ---------------------------------------------------------------------------
+// Exact n / d for 0 <= n < 2^22 with a precomputed float reciprocal: the estimate is off by at most
+// one, which the remainder test repairs.  Replaces ~20-instruction integer divisions by run-time
+// divisors in the per-pass decode.
+__device__ __forceinline__ int fast_div(int n, int d, float inv_d, int &rem) {
+  int q = (int)((float)n * inv_d);
+  int r = n - q * d;
+  if (r < 0) {
+    --q;
+    r += d;
+  } else if (r >= d) {
+    ++q;
+    r -= d;
+  }
+  rem = r;
+  return q;
+}
+
 struct TileSetup {
   LevelGeom lv[kMaxLevelsSmem];
   int tile_first[kMaxLevelsSmem + 1];  // first tile index of each level (tiled order)
+  int tiles_x[kMaxLevelsSmem];         // tiles per row of each level
+  float inv_tiles_x[kMaxLevelsSmem];
   int n_tiles;                         // tiles per image
   int tiled;                           // 1 = 2-D tiles, 0 = linear chunks
 };
@@ -436,7 +523,7 @@ struct TileSetup {
 __device__ __forceinline__ void setup_tiles(const MsdaParams &p, TileSetup &ts) {
   // executed by warp 0 of the CTA (all 32 lanes); L <= kMaxLevelsSmem <= 32 guaranteed by the host.
   // Lane l loads level l (the loads of all levels are in flight together), then two warp scans
-  // give each level its first query and first tile.
+  // give each level its first query and first tile.  Tile extents are powers of two (shifts).
   const int l = threadIdx.x;
   int H = 0, W = 0, start = 0;
   if (l < p.L) {
@@ -445,7 +532,9 @@ __device__ __forceinline__ void setup_tiles(const MsdaParams &p, TileSetup &ts) 
     start = (int)__ldg(p.starts + l);
   }
   const int nq = H * W;
-  const int nt = (l < p.L) ? ((H + p.tile_h - 1) / p.tile_h) * ((W + p.tile_w - 1) / p.tile_w) : 0;
+  const int tx = (W + (1 << p.tile_w_log2) - 1) >> p.tile_w_log2;
+  const int ty = (H + (1 << p.tile_h_log2) - 1) >> p.tile_h_log2;
+  const int nt = (l < p.L) ? tx * ty : 0;
   int qs = nq, tsum = nt;  // inclusive scans
 #pragma unroll
   for (int off = 1; off < 32; off <<= 1) {
@@ -462,58 +551,37 @@ __device__ __forceinline__ void setup_tiles(const MsdaParams &p, TileSetup &ts) 
     ts.lv[l].start = start;
     ts.lv[l].qstart = qs - nq;
     ts.tile_first[l] = tsum - nt;
+    ts.tiles_x[l] = tx > 0 ? tx : 1;
+    ts.inv_tiles_x[l] = 1.0f / (float)(tx > 0 ? tx : 1);
   }
   const int q_total = __shfl_sync(0xffffffffu, qs, 31);
   const int t_total = __shfl_sync(0xffffffffu, tsum, 31);
   if (l == 0) {
     ts.tile_first[p.L] = t_total;
-    const int tq = p.tile_w * p.tile_h;
+    const int tq_log2 = p.tile_w_log2 + p.tile_h_log2;
     if (p.want_tiled && q_total == p.Q) {
       ts.tiled = 1;
       ts.n_tiles = t_total;
     } else {
       ts.tiled = 0;
-      ts.n_tiles = (p.Q + tq - 1) / tq;
+      ts.n_tiles = (p.Q + (1 << tq_log2) - 1) >> tq_log2;
     }
   }
 }
 
-// Maps (tile, slot-in-tile) to a query index, or -1 for a padding slot.
-struct TileCursor {
-  int q0;       // linear: first query of the tile
-  int lvl_q0;   // tiled: first query of the level
-  int y0, x0;   // tiled: top-left pixel of the tile
-  int H, W;     // tiled: level extent
-};
-
-__device__ __forceinline__ TileCursor open_tile(const MsdaParams &p, const TileSetup &ts, int t) {
-  TileCursor c;
+// Maps (tile t, query slot tq inside the tile) to a query index, or -1 for a padding slot.
+__device__ __forceinline__ int tile_query(const MsdaParams &p, const TileSetup &ts, int t, int tq) {
   if (!ts.tiled) {
-    c.q0 = t * p.tile_w * p.tile_h;
-    c.lvl_q0 = 0;
-    c.y0 = c.x0 = c.H = c.W = 0;
-    return c;
+    const int q = (t << (p.tile_w_log2 + p.tile_h_log2)) + tq;
+    return q < p.Q ? q : -1;
   }
   int l = 0;
   while (l + 1 < p.L && t >= ts.tile_first[l + 1]) ++l;
-  const int tl = t - ts.tile_first[l];
-  const int tiles_x = (ts.lv[l].W + p.tile_w - 1) / p.tile_w;
-  c.q0 = 0;
-  c.lvl_q0 = ts.lv[l].qstart;
-  c.y0 = (tl / tiles_x) * p.tile_h;
-  c.x0 = (tl % tiles_x) * p.tile_w;
-  c.H = ts.lv[l].H;
-  c.W = ts.lv[l].W;
-  return c;
-}
-
-__device__ __forceinline__ int tile_query(const MsdaParams &p, const TileSetup &ts, const TileCursor &c, int tq) {
-  if (!ts.tiled) {
-    const int q = c.q0 + tq;
-    return q < p.Q ? q : -1;
-  }
-  const int y = c.y0 + tq / p.tile_w, x = c.x0 + tq % p.tile_w;
-  return (y < c.H && x < c.W) ? c.lvl_q0 + y * c.W + x : -1;
+  int tcol;
+  const int trow = fast_div(t - ts.tile_first[l], ts.tiles_x[l], ts.inv_tiles_x[l], tcol);
+  const int y = (trow << p.tile_h_log2) + (tq >> p.tile_w_log2);
+  const int x = (tcol << p.tile_w_log2) + (tq & ((1 << p.tile_w_log2) - 1));
+  return (y < ts.lv[l].H && x < ts.lv[l].W) ? ts.lv[l].qstart + y * ts.lv[l].W + x : -1;
 }
 
 // ---------------------------------------------------------------------------
@@ -527,13 +595,14 @@ __device__ __forceinline__ int tile_query(const MsdaParams &p, const TileSetup &
 //   MATH  kExact: fp32 weights ; kFhfma: 16-bit weights + FHFMA
 // ---------------------------------------------------------------------------
 template <typename T, int D, int P_T, int SPLIT, int MATH>
-__global__ void __launch_bounds__(kThreads, 2) msda_fwd_vec(const MsdaParams p) {
+__global__ void __launch_bounds__(kThreads, MSDA_MINB) msda_fwd_vec(const MsdaParams p) {
   constexpr int E = (int)sizeof(T);
   constexpr int VEC = 16 / E;            // channels per lane
   constexpr int G = D / VEC;             // lanes per corner row
   constexpr int GS = G * SPLIT;          // lanes per (query, head) pair
   constexpr int PPW = 32 / GS;           // pairs per warp
   constexpr int PAIRS_PER_PASS = kThreads / GS;
+  constexpr int NB = MSDA_NB;            // samples consumed per batch in the broadcast path
   static_assert(D % VEC == 0 && GS <= 32 && (GS & (GS - 1)) == 0, "unsupported D / SPLIT");
 
   __shared__ TileSetup ts;
@@ -548,125 +617,152 @@ __global__ void __launch_bounds__(kThreads, 2) msda_fwd_vec(const MsdaParams p) 
   const int P = P_T ? P_T : p.P;
   const int LP = p.L * P;
   const int M = p.M;
-  const size_t pix_bytes = (size_t)M * D * E;
+  const unsigned pix_bytes = (unsigned)(M * D * E);
   const int lane_in_pair = threadIdx.x % GS;
   const int sub = lane_in_pair % G;     // which 16-byte piece of the row
   const int split = lane_in_pair / G;   // which share of the points
-  const int slot0 = threadIdx.x / GS;
-  const int tile_q = p.tile_w * p.tile_h;
-  const int slots = tile_q * M;
-  const int64_t work = (int64_t)p.B * ts.n_tiles;
+  const int slots = M << (p.tile_w_log2 + p.tile_h_log2);
+  // one loop iteration = one pass of the CTA over PAIRS_PER_PASS (query, head) pairs of one tile of
+  // image blockIdx.y; the host guarantees that the pass count stays below 2^22
+  const int total = ts.n_tiles * p.passes;
+  const int b = blockIdx.y;
 
-  for (int64_t wi = blockIdx.x; wi < work; wi += gridDim.x) {
-    const int b = (int)(wi / ts.n_tiles);
-    const int t = (int)(wi - (int64_t)b * ts.n_tiles);
-    const TileCursor cur = open_tile(p, ts, t);
-    const char *vb = value + (size_t)b * p.S * pix_bytes + (size_t)sub * 16;
-
-    for (int s = slot0; s < slots; s += PAIRS_PER_PASS) {
-      int tq, m;
+  for (int w = blockIdx.x; w < total; w += gridDim.x) {
+    int q, m;
+    {
+      int pass;
+      const int t = fast_div(w, p.passes, p.inv_passes, pass);
+      const int s = pass * PAIRS_PER_PASS + (int)(threadIdx.x / GS);
+      int tq;
       if (p.head_major) {
-        const int qb = s / (PPW * M), r = s - qb * (PPW * M);
-        m = r / PPW;
-        tq = qb * PPW + (r - m * PPW);
+        // slots ordered [query block of PPW][head][query in block]: a warp holds one head of PPW
+        // neighbouring queries
+        const int g = s & (PPW - 1);
+        const int qb = fast_div(s / PPW, M, p.inv_M, m);
+        tq = qb * PPW + g;
       } else {
-        tq = s / M;
-        m = s - tq * M;
+        tq = fast_div(s, M, p.inv_M, m);
       }
-      const int q = tile_query(p, ts, cur, tq);
-      // a pair is handled by GS consecutive lanes, so this branch never splits a lane group;
-      // the shuffles below only cross lanes of the same pair
-      if (q < 0) continue;
-
-      const int64_t pair = ((int64_t)b * p.Q + q) * M + m;
+      q = (s < slots) ? tile_query(p, ts, t, tq) : -1;
+    }
+    // Padding slots (tile edge, tail of the last pass) stay in the loop with all their weights forced
+    // to zero instead of branching out: the warp stays converged, so the shuffles below can name all 32
+    // lanes with a compile-time mask.  They read the inputs of pair 0 (always present) and store nothing.
+    const bool live = q >= 0;
+    {
+      const int64_t pair = live ? ((int64_t)b * p.Q + q) * M + m : 0;
       const T *lp = loc + pair * LP * 2;
       const T *wp = wgt + pair * LP;
-      const char *vm = vb + (size_t)m * D * E;
+      const char *vm = value + ((size_t)b * p.S * M + m) * (size_t)(D * E) + (size_t)sub * 16;
 
       float acc[VEC];
 #pragma unroll
       for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
 
-      for (int l = 0; l < p.L; ++l) {
-        const int H = ts.lv[l].H, W = ts.lv[l].W;
-        const char *vl = vm + (size_t)ts.lv[l].start * pix_bytes;
-
-        if constexpr (P_T == 4 && SPLIT == 1) {
-          // all four points of the level: one vector load of locations, one of weights
-          float xs[4], ys[4], aws[4];
-          if constexpr (E == 2) {
-            const uint4 lraw = ldg128(lp + l * 8);
-            const uint2 wraw = __ldg(reinterpret_cast<const uint2 *>(wp + l * 4));
-            const unsigned lw[4] = {lraw.x, lraw.y, lraw.z, lraw.w};
-            const unsigned ww[2] = {wraw.x, wraw.y};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const float2 xy = unpack2<T>(lw[k]);
-              const float2 a2 = unpack2<T>(ww[k / 2]);
-              xs[k] = xy.x;
-              ys[k] = xy.y;
-              aws[k] = (k & 1) ? a2.y : a2.x;
-            }
-          } else {
-            const float4 l0 = __ldg(reinterpret_cast<const float4 *>(lp + l * 8));
-            const float4 l1 = __ldg(reinterpret_cast<const float4 *>(lp + l * 8 + 4));
-            const float4 w4 = __ldg(reinterpret_cast<const float4 *>(wp + l * 4));
-            xs[0] = l0.x; ys[0] = l0.y; xs[1] = l0.z; ys[1] = l0.w;
-            xs[2] = l1.x; ys[2] = l1.y; xs[3] = l1.z; ys[3] = l1.w;
-            aws[0] = w4.x; aws[1] = w4.y; aws[2] = w4.z; aws[3] = w4.w;
+      if constexpr (P_T == 4 && SPLIT == 1 && G >= 4) {
+        // ---- broadcast path: lane (sub & 3) of the group works out the geometry of sample (sub & 3)
+        // of the level once, the G lanes that consume it receive it by warp shuffle.  Everything that
+        // must not contribute (corner outside the level, sample outside the range test) has weight
+        // zero, and a zero weight predicates both the load and the FMAs of that corner off.
+        constexpr unsigned group_mask = 0xffffffffu;
+        const int ks = sub & 3;
+        float nx, ny, naw;
+        load_sample_inputs<T>(lp, wp, ks, nx, ny, naw);
+        for (int l = 0; l < p.L; ++l) {
+          const int H = ts.lv[l].H, W = ts.lv[l].W;
+          const float x = nx, y = ny, aw = live ? naw : 0.f;
+          if (l + 1 < p.L) load_sample_inputs<T>(lp, wp, (l + 1) * 4 + ks, nx, ny, naw);  // prefetch next level
+          int i00;
+          float cw[4];
+          make_geo(x, y, aw, H, W, i00, cw);
+          i00 += ts.lv[l].start;
+          unsigned pk0 = 0, pk1 = 0;
+          if constexpr (MATH == kFhfma) {
+            pk0 = pack_weights<T>(cw[0], cw[1]);
+            pk1 = pack_weights<T>(cw[2], cw[3]);
           }
-          Sample<float> sm[4];
-          uint4 rows[4][4];
+          // consume the four samples NB at a time: NB*4 row loads in flight per lane
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            sm[k] = make_sample<float>(xs[k], ys[k], aws[k], H, W);
+          for (int k0 = 0; k0 < 4; k0 += NB) {
+            uint4 rows[NB][4];
+            float bw[NB][4];
+            unsigned bp[NB][2];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              rows[k][j] = make_uint4(0u, 0u, 0u, 0u);
-              if (sm[k].ok[j]) rows[k][j] = ldg128(vl + (size_t)sm[k].idx[j] * pix_bytes);
+            for (int kk = 0; kk < NB; ++kk) {
+              const int k = k0 + kk;
+              const int bi = __shfl_sync(group_mask, i00, k, G);
+              if constexpr (MATH == kFhfma) {
+                bp[kk][0] = __shfl_sync(group_mask, pk0, k, G);
+                bp[kk][1] = __shfl_sync(group_mask, pk1, k, G);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) bw[kk][j] = __shfl_sync(group_mask, cw[j], k, G);
+              }
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int idx = bi + (j & 1) + ((j & 2) ? W : 0);
+                bool on;
+                if constexpr (MATH == kFhfma) on = ((bp[kk][j >> 1] >> ((j & 1) * 16)) & 0x7fffu) != 0u;
+                else on = bw[kk][j] != 0.f;
+                if (on) rows[kk][j] = ldg128(vm + (size_t)(unsigned)idx * pix_bytes);
+              }
+            }
+#pragma unroll
+            for (int kk = 0; kk < NB; ++kk) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                if constexpr (MATH == kFhfma) {
+                  const unsigned w16 = (bp[kk][j >> 1] >> ((j & 1) * 16)) & 0xffffu;
+                  if ((w16 & 0x7fffu) != 0u) RowFma<T, kFhfma>::run(acc, rows[kk][j], 0.f, w16);
+                } else {
+                  if (bw[kk][j] != 0.f) RowFma<T, kExact>::run(acc, rows[kk][j], bw[kk][j], 0u);
+                }
+              }
             }
           }
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              RowFma<T, MATH>::run(acc, rows[k][j], sm[k].cw[j], MATH == kFhfma ? weight_to_16<T>(sm[k].cw[j]) : 0u);
-            }
-          }
-        } else {
-          // run-time P and/or split points: scalar loads of the location / weight
+        }
+      } else {
+        // ---- run-time P, split points, or rows narrower than four lanes: every lane works out the
+        // geometry of the samples it consumes
+        for (int l = 0; l < p.L; ++l) {
+          const int H = ts.lv[l].H, W = ts.lv[l].W;
+          const char *vl = vm + (size_t)ts.lv[l].start * pix_bytes;
           for (int k = split; k < P; k += SPLIT) {
-            const int si = l * P + k;
-            const float x = Elem<T>::to_acc(lp[si * 2]);
-            const float y = Elem<T>::to_acc(lp[si * 2 + 1]);
-            const float aw = Elem<T>::to_acc(wp[si]);
-            const Sample<float> sm = make_sample<float>(x, y, aw, H, W);
+            float x, y, aw;
+            load_sample_inputs<T>(lp, wp, l * P + k, x, y, aw);
+            aw = live ? aw : 0.f;
+            int i00;
+            float cw[4];
+            make_geo(x, y, aw, H, W, i00, cw);
             uint4 rows[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              rows[j] = make_uint4(0u, 0u, 0u, 0u);
-              if (sm.ok[j]) rows[j] = ldg128(vl + (size_t)sm.idx[j] * pix_bytes);
+              const int idx = i00 + (j & 1) + ((j & 2) ? W : 0);
+              if (cw[j] != 0.f) rows[j] = ldg128(vl + (size_t)(unsigned)idx * pix_bytes);
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              RowFma<T, MATH>::run(acc, rows[j], sm.cw[j], MATH == kFhfma ? weight_to_16<T>(sm.cw[j]) : 0u);
+              if (cw[j] != 0.f) {
+                if constexpr (MATH == kFhfma) {
+                  const unsigned w16 = weight_to_16<T>(cw[j]);
+                  RowFma<T, kFhfma>::run(acc, rows[j], 0.f, w16);
+                } else {
+                  RowFma<T, kExact>::run(acc, rows[j], cw[j], 0u);
+                }
+              }
             }
           }
         }
       }
 
       if constexpr (SPLIT > 1) {
-        // only the GS lanes of this pair are named in the mask: other pairs of the warp may have
-        // left the loop already
-        const unsigned lane = threadIdx.x & 31u;
-        const unsigned pair_mask = (GS == 32) ? 0xffffffffu : (((1u << GS) - 1u) << (lane & ~(unsigned)(GS - 1)));
 #pragma unroll
         for (int off = G; off < GS; off <<= 1) {
 #pragma unroll
-          for (int i = 0; i < VEC; ++i) acc[i] += __shfl_xor_sync(pair_mask, acc[i], off);
+          for (int i = 0; i < VEC; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], off);
         }
       }
-      if (split == 0) store_row<T, VEC>(out + pair * D + sub * VEC, acc);
+      if (live && split == 0) store_row<T, VEC>(out + pair * D + sub * VEC, acc);
     }
   }
 }
@@ -745,12 +841,12 @@ int launch_generic(const MsdaParams &p, cudaStream_t stream) {
 struct VecPlan {
   int split;
   int math;
-  unsigned grid;
+  unsigned grid, grid_y;
 };
 
 template <typename T, int D, int P_T, int SPLIT, int MATH>
-int launch_vec_inst(const MsdaParams &p, unsigned grid, cudaStream_t stream) {
-  msda_fwd_vec<T, D, P_T, SPLIT, MATH><<<grid, kThreads, 0, stream>>>(p);
+int launch_vec_inst(const MsdaParams &p, const VecPlan &plan, cudaStream_t stream) {
+  msda_fwd_vec<T, D, P_T, SPLIT, MATH><<<dim3(plan.grid, plan.grid_y, 1), kThreads, 0, stream>>>(p);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return (int)cudaGetLastError();
 }
@@ -760,12 +856,12 @@ int launch_vec_d(const MsdaParams &p, const VecPlan &plan, cudaStream_t stream) 
   constexpr int G = D * (int)sizeof(T) / 16;
   if (plan.split == 4) {
     if constexpr (G * 4 <= 32) {
-      return p.P == 4 ? launch_vec_inst<T, D, 4, 4, MATH>(p, plan.grid, stream)
-                      : launch_vec_inst<T, D, 0, 4, MATH>(p, plan.grid, stream);
+      return p.P == 4 ? launch_vec_inst<T, D, 4, 4, MATH>(p, plan, stream)
+                      : launch_vec_inst<T, D, 0, 4, MATH>(p, plan, stream);
     }
   }
-  return p.P == 4 ? launch_vec_inst<T, D, 4, 1, MATH>(p, plan.grid, stream)
-                  : launch_vec_inst<T, D, 0, 1, MATH>(p, plan.grid, stream);
+  return p.P == 4 ? launch_vec_inst<T, D, 4, 1, MATH>(p, plan, stream)
+                  : launch_vec_inst<T, D, 0, 1, MATH>(p, plan, stream);
 }
 
 template <typename T>
@@ -789,6 +885,19 @@ int launch_vec_t(const MsdaParams &p, const VecPlan &plan, cudaStream_t stream) 
   }
 }
 
+int run_generic(const MsdaParams &p, int dtype, cudaStream_t stream) {
+  int rc;
+  switch (dtype) {
+    case MSDA_F32: rc = launch_generic<float>(p, stream); break;
+    case MSDA_F16: rc = launch_generic<__half>(p, stream); break;
+    case MSDA_BF16: rc = launch_generic<__nv_bfloat16>(p, stream); break;
+    case MSDA_F64: rc = launch_generic<double>(p, stream); break;
+    default: return MSDA_ERR_BAD_DTYPE;
+  }
+  if (rc == 0) snprintf(g_last_variant, sizeof(g_last_variant), "generic<%s>%s", dtype_name(dtype), p.ref_dim ? "/fused" : "");
+  return rc;
+}
+
 bool aligned_to(const void *ptr, size_t a) { return (reinterpret_cast<uintptr_t>(ptr) % a) == 0; }
 
 int forward_impl(MsdaParams p, int dtype, unsigned flags, cudaStream_t stream) {
@@ -805,18 +914,7 @@ int forward_impl(MsdaParams p, int dtype, unsigned flags, cudaStream_t stream) {
     vec_ok = aligned_to(p.loc, 16) && aligned_to(p.weight, E == 2 ? 8 : 16);
   }
 
-  if (!vec_ok) {
-    int rc;
-    switch (dtype) {
-      case MSDA_F32: rc = launch_generic<float>(p, stream); break;
-      case MSDA_F16: rc = launch_generic<__half>(p, stream); break;
-      case MSDA_BF16: rc = launch_generic<__nv_bfloat16>(p, stream); break;
-      case MSDA_F64: rc = launch_generic<double>(p, stream); break;
-      default: return MSDA_ERR_BAD_DTYPE;
-    }
-    if (rc == 0) snprintf(g_last_variant, sizeof(g_last_variant), "generic<%s>%s", dtype_name(dtype), fused ? "/fused" : "");
-    return rc;
-  }
+  if (!vec_ok) return run_generic(p, dtype, stream);
 
   VecPlan plan;
   const int sms = sm_count();
@@ -834,35 +932,45 @@ int forward_impl(MsdaParams p, int dtype, unsigned flags, cudaStream_t stream) {
   }
 
   const int ppw = 32 / (G * plan.split);
-  // tile geometry: width a multiple of the pairs a warp holds in head-major order
+  const int pairs_per_pass = kThreads / (G * plan.split);
+  auto ceil_log2 = [](int v) { int l = 0; while ((1 << l) < v) ++l; return l; };
+  // tile geometry: power-of-two extents, width at least the pairs a warp holds in head-major order
   p.want_tiled = (flags & MSDA_FLAG_LINEAR_ORDER) ? 0 : (p.Q == p.S ? 1 : 0);
   p.head_major = env_int("MSDA_B200_HEAD_MAJOR", 1);
-  p.tile_w = env_int("MSDA_B200_TILE_W", 8);
-  p.tile_h = env_int("MSDA_B200_TILE_H", p.want_tiled ? 4 : 1);
-  if (p.tile_w < ppw) p.tile_w = ppw;
-  p.tile_w = (p.tile_w + ppw - 1) / ppw * ppw;
-  if (p.tile_h < 1) p.tile_h = 1;
+  int tile_w = env_int("MSDA_B200_TILE_W", 8);
+  int tile_h = env_int("MSDA_B200_TILE_H", p.want_tiled ? 4 : 1);
   if (!p.want_tiled) {
-    // linear chunks: one pass of the CTA per tile unless the problem is large
-    const int pairs_per_pass = kThreads / (G * plan.split);
-    int tq = (pairs_per_pass + p.M - 1) / p.M;
-    tq = (tq + ppw - 1) / ppw * ppw;
-    p.tile_w = tq;
-    p.tile_h = 1;
+    // linear chunks: about one pass of the CTA per chunk
+    tile_w = (pairs_per_pass + p.M - 1) / p.M;
+    tile_h = 1;
   }
+  if (tile_w < ppw) tile_w = ppw;
+  if (tile_h < 1) tile_h = 1;
+  p.tile_w_log2 = ceil_log2(tile_w);
+  p.tile_h_log2 = ceil_log2(tile_h);
+  if (p.tile_w_log2 + p.tile_h_log2 > 12) return MSDA_ERR_UNSUPPORTED;
+  const int64_t tile_q = (int64_t)1 << (p.tile_w_log2 + p.tile_h_log2);
+  const int64_t passes = (tile_q * p.M + pairs_per_pass - 1) / pairs_per_pass;
+  p.passes = (int)passes;
+  p.inv_passes = 1.0f / (float)passes;
+  p.inv_M = 1.0f / (float)p.M;
 
-  // grid: enough CTAs to cover every tile once, capped at a few waves (grid-stride loop inside)
-  const int64_t tile_q = (int64_t)p.tile_w * p.tile_h;
-  // The level shapes are device-resident, so the exact 2-D tile count is unknown here.  The
-  // kernel strides over the real count, so an estimate is enough: interior tiles plus an
-  // allowance for the partial tiles on the right/bottom edge of each level.
+  // grid: x strides over the (tile, pass) units of one image, y = image.  The level shapes are
+  // device-resident, so the exact 2-D tile count is unknown here; the kernel strides over the real
+  // count, so an estimate (interior tiles plus an allowance for the partial tiles on the right/bottom
+  // edge of each level) is enough.
   int64_t tiles_est = (p.Q + tile_q - 1) / tile_q;
   if (p.want_tiled) tiles_est += tiles_est / 4 + 4 * p.L;
-  int64_t grid = (int64_t)p.B * tiles_est;
-  const int64_t cap = (int64_t)sms * env_int("MSDA_B200_CTAS_PER_SM", 16);
+  // fast_div needs every dividend below 2^22; worst case of the real tile count: one query per tile
+  if ((int64_t)p.Q * passes >= ((int64_t)1 << 22) || tile_q * p.M >= ((int64_t)1 << 22) || p.B > 65535) {
+    return run_generic(p, dtype, stream);
+  }
+  int64_t grid = tiles_est * passes;
+  const int64_t cap = ((int64_t)sms * env_int("MSDA_B200_CTAS_PER_SM", 32) + p.B - 1) / p.B;
   if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;
   plan.grid = (unsigned)grid;
+  plan.grid_y = (unsigned)p.B;
 
   int rc;
   switch (dtype) {
@@ -873,7 +981,7 @@ int forward_impl(MsdaParams p, int dtype, unsigned flags, cudaStream_t stream) {
   }
   if (rc == 0) {
     snprintf(g_last_variant, sizeof(g_last_variant), "vec<%s,D%d,P%d,split%d>/%s%dx%d/%s/%s", dtype_name(dtype), p.D,
-             p.P == 4 ? 4 : 0, plan.split, p.want_tiled ? "tiled" : "linear", p.tile_w, p.tile_h,
+             p.P == 4 ? 4 : 0, plan.split, p.want_tiled ? "tiled" : "linear", 1 << p.tile_w_log2, 1 << p.tile_h_log2,
              p.head_major ? "head-major" : "query-major", plan.math == kFhfma ? "fhfma" : "exact");
   }
   return rc;

@@ -47,3 +47,21 @@ def shard_batch(tensors, rank: int, world_size: int):
 def weak_scaling_images(per_gpu_batch: int, world_size: int) -> int:
     """Weak scaling: per-GPU work is fixed, the job's image count grows with the GPU count."""
     return per_gpu_batch * world_size
+
+
+def aggregate_throughput(elapsed_ms: float, images_this_rank: int, device=None):
+    """Whole-job throughput from per-rank device timings: the job takes as long as its slowest rank
+    (MAX over ranks of the CUDA-event time), and processes the SUM of the ranks' images.  Uses the
+    default ``torch.distributed`` group when one is initialised (NCCL on GPUs, gloo in the CPU tests);
+    this accounting reduction is the only collective of the path -- the data path itself has none.
+    Returns ``(images_per_s, max_elapsed_ms, total_images)``."""
+    import torch
+    import torch.distributed as dist
+
+    t = torch.tensor([float(elapsed_ms)], dtype=torch.float64, device=device)
+    n = torch.tensor([int(images_this_rank)], dtype=torch.int64, device=device)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(n, op=dist.ReduceOp.SUM)
+    max_ms, total = float(t.item()), int(n.item())
+    return (total / (max_ms * 1e-3) if max_ms > 0 else float("inf")), max_ms, total

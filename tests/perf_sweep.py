@@ -70,6 +70,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "sweep.json"))
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--only", default=None, help="'headline': headline + decoder rows with a short config list")
+    ap.add_argument("--no-probes", action="store_true")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     torch.cuda.set_device(dev)
@@ -79,7 +81,7 @@ def main():
 
     # ---- read probes: L2 (working set << L2) and HBM (working set >> L2) ----
     sink = torch.zeros(4, dtype=torch.int32, device=dev)
-    for mb, reps in ((8, 64), (32, 32), (64, 16), (96, 12), (512, 2), (2048, 1)):
+    for mb, reps in (() if args.no_probes else ((8, 64), (32, 32), (64, 16), (96, 12), (512, 2), (2048, 1))):
         buf = torch.empty(mb * 1024 * 1024, dtype=torch.uint8, device=dev).random_(0, 255)
         lib = cb._native.load()
         stream = torch.cuda.current_stream().cuda_stream
@@ -108,6 +110,9 @@ def main():
                  ("ref_test_mid_fp32", 1, "float32", None)]
     if args.quick:
         workloads = workloads[:2]
+    if args.only == "headline":
+        workloads = [("swinl_enc_1152x768", 1, "float16", None), ("swinl_enc_1152x768", 1, "float32", None),
+                     ("swinl_dec_1152x768", 1, "float16", None), ("swinl_enc_1920x1280", 2, "float16", None)]
     base_cfgs = [
         {"name": "default", "flags": 0},
         {"name": "fhfma", "flags": cb.FLAG_MATH_FHFMA},
@@ -118,7 +123,7 @@ def main():
         {"name": "generic", "flags": cb.FLAG_FORCE_GENERIC},
     ]
     tile_cfgs = [{"name": f"tile{w}x{h}+fhfma", "flags": cb.FLAG_MATH_FHFMA, "MSDA_B200_TILE_W": w, "MSDA_B200_TILE_H": h}
-                 for (w, h) in ((8, 1), (8, 2), (8, 8), (16, 2), (16, 4), (16, 8), (24, 4), (32, 2))]
+                 for (w, h) in ((8, 1), (8, 2), (8, 8), (16, 2), (16, 4), (4, 4), (32, 2), (32, 8))]
     split_cfgs = [{"name": f"split{s}", "flags": 0, "MSDA_B200_SPLIT": s} for s in (1, 4)]
     split_cfgs += [{"name": f"split{s}+fhfma", "flags": cb.FLAG_MATH_FHFMA, "MSDA_B200_SPLIT": s} for s in (1, 4)]
 
@@ -136,6 +141,10 @@ def main():
             cfgs += split_cfgs
         if dtn == "float32":
             cfgs = [c for c in cfgs if "fhfma" not in c["name"]]
+        if args.only == "headline":
+            cfgs = [c for c in cfgs if c["name"] in ("default", "fhfma", "linear+fhfma", "query-major", "tile8x8+fhfma", "tile16x4+fhfma",
+                                                      "tile4x4+fhfma", "split1", "split4", "split1+fhfma")]
+            have_ref = False
         for cfg in cfgs:
             set_env(cfg)
             calls = [cb.PreparedForward(*(s[k] for k in KEYS), flags=cfg["flags"]) for s in sets]

@@ -13,6 +13,8 @@ for st in $STAGES; do
       tail -5 gpurun_out/pytest_gpu.log ;;
     smoke)
       timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke exit $?"; tail -5 gpurun_out/smoke.log ;;
+    variants)
+      bash tests/perf_variants.sh > /dev/null 2>&1; echo "variants exit $?"; tail -5 gpurun_out/variants.log ;;
     sweep)
       timeout 900 python tests/perf_sweep.py --out gpurun_out/sweep.json > gpurun_out/sweep.log 2>&1; echo "sweep exit $?"; tail -3 gpurun_out/sweep.log ;;
     bench)
