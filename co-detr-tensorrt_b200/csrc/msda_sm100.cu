@@ -57,10 +57,10 @@ namespace {
 constexpr int kMaxLevelsSmem = 16;  // levels cached in shared memory by the fast kernels
 constexpr int kThreads = 256;
 #ifndef MSDA_MINB
-#define MSDA_MINB 3
+#define MSDA_MINB 4
 #endif
 #ifndef MSDA_NB
-#define MSDA_NB 2
+#define MSDA_NB 1
 #endif
 
 std::atomic<uint64_t> g_launch_count{0};
@@ -654,6 +654,9 @@ __global__ void __launch_bounds__(kThreads, MSDA_MINB) msda_fwd_vec(const MsdaPa
       const T *lp = loc + pair * LP * 2;
       const T *wp = wgt + pair * LP;
       const char *vm = value + ((size_t)b * p.S * M + m) * (size_t)(D * E) + (size_t)sub * 16;
+      // keep the row base as one opaque 64-bit register pair: every corner address is then a single
+      // IMAD.WIDE (index * pixel pitch + base) instead of a re-derivation from the kernel parameters
+      asm volatile("" : "+l"(vm));
 
       float acc[VEC];
 #pragma unroll

@@ -24,7 +24,9 @@ for st in $STAGES; do
       timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches.csv \
         python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1; echo "ncu launches exit $?"
       timeout 600 ncu --set full --clock-control none --import-source on -k regex:msda_fwd -s 6 -c 2 -f -o gpurun_out/prof_headline \
-        python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_full.log 2>&1; echo "ncu full exit $?" ;;
+        python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_full.log 2>&1; echo "ncu full exit $?"
+      timeout 600 ncu --set full --clock-control none --import-source on -k regex:msda_fwd -s 6 -c 2 -f -o gpurun_out/prof_headline_fhfma \
+        python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e --flags 4 > gpurun_out/ncu_full_fhfma.log 2>&1; echo "ncu full fhfma exit $?" ;;
   esac
 done
 ls -la gpurun_out | tail -20
