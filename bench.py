@@ -364,6 +364,15 @@ def run_b200(args):
         "gather_bytes_per_launch": gather_bytes, "gather_GBps": gather_bytes / launch_s / 1e9,
     }
 
+    # second roofline: the no-reuse gather volume (every corner row fetched separately) against the
+    # L2->SM read bandwidth measured live with the library's read probe (48 MB working set, L2-resident)
+    l2_peak = cb.read_bandwidth_probe(dev, 48 * 1024 * 1024, 24)
+    roofline_l2 = {
+        "bound": "l2_gather", "achieved": gather_bytes / launch_s / 1e9, "peak": l2_peak, "unit": "GB/s",
+        "frac": gather_bytes / launch_s / 1e9 / l2_peak, "bytes_per_launch": gather_bytes,
+        "peak_source": "msda_b200_read_probe, 48 MB working set, measured in this run",
+    }
+
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         ips, ms, cores, sample, _ = cpu_reference_leg(wl, batch, args.loc_mode, args.cpu_seconds)
@@ -380,7 +389,7 @@ def run_b200(args):
             "l2_policy": f"rotating {n_sets} distinct input sets, {n_sets * hbm_bytes / 1e6:.0f} MB > 126 MB L2",
             "launch": "cuda_graph" if graph is not None else "C ABI via ctypes, back to back on one stream",
         },
-        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+        "roofline": roofline, "roofline_l2_gather": roofline_l2, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
         "clocks": sampler.summary(),
     }
 

@@ -9,17 +9,17 @@ Importing the package loads ``csrc/libmsda_b200.so`` and registers
 the library has not been built: there is no CPU or PyTorch fallback.
 """
 from . import _native
-from ._native import (FLAG_FORCE_GENERIC, FLAG_LINEAR_ORDER, FLAG_MATH_EXACT, FLAG_MATH_FHFMA, FLAG_NO_STAGING,
+from ._native import (FLAG_FORCE_GENERIC, FLAG_LINEAR_ORDER, FLAG_MATH_EXACT, FLAG_MATH_FHFMA, FLAG_NO_STAGING, FLAG_STAGE_TMA,
                       NativeLibraryError, build_native, last_variant, launch_count)
 from . import workloads
 from . import sharding
 from . import ops
 from .ops import (HostForward, PreparedForward, forward_fused, forward_into, multi_scale_deformable_attention, plugin_enqueue,
-                  set_default_flags)
+                  read_bandwidth_probe, set_default_flags)
 
 __all__ = [
     "multi_scale_deformable_attention", "forward_into", "forward_fused", "plugin_enqueue", "HostForward", "PreparedForward",
-    "set_default_flags", "build_native", "launch_count", "last_variant", "workloads", "sharding",
-    "FLAG_FORCE_GENERIC", "FLAG_LINEAR_ORDER", "FLAG_MATH_EXACT", "FLAG_MATH_FHFMA", "FLAG_NO_STAGING",
+    "set_default_flags", "read_bandwidth_probe", "build_native", "launch_count", "last_variant", "workloads", "sharding",
+    "FLAG_FORCE_GENERIC", "FLAG_LINEAR_ORDER", "FLAG_MATH_EXACT", "FLAG_MATH_FHFMA", "FLAG_NO_STAGING", "FLAG_STAGE_TMA",
     "NativeLibraryError",
 ]

@@ -53,6 +53,7 @@ FLAG_LINEAR_ORDER = 1 << 1
 FLAG_MATH_FHFMA = 1 << 2
 FLAG_MATH_EXACT = 1 << 3
 FLAG_NO_STAGING = 1 << 4
+FLAG_STAGE_TMA = 1 << 5
 
 
 class NativeLibraryError(RuntimeError):

@@ -115,6 +115,8 @@ struct MsdaParams {
   int tile_w_log2, tile_h_log2;  // query tile is 2^tile_w_log2 x 2^tile_h_log2 (tiled) or that many consecutive queries (linear)
   int passes;           // CTA passes per tile = ceil(tile queries * M / pairs per pass)
   float inv_passes, inv_M;       // reciprocals for fast_div
+  int qpp;              // queries per pass when PAIRS_PER_PASS is a whole number of queries, else 0
+  int stage_loc_row, stage_w_row;  // padded shared-memory row pitch (bytes) of one query's locations / weights
   int want_tiled;       // 1: use 2-D tiles when sum(H*W) == Q
   int head_major;       // 1: a warp holds one head of 32/G neighbouring queries
 };
@@ -439,6 +441,23 @@ __device__ __forceinline__ void load_sample_inputs(const T *lp, const T *wp, int
   }
 }
 
+// same, from the shared-memory staging rows of the pair (generic loads: LDS)
+template <typename T>
+__device__ __forceinline__ void load_sample_inputs_smem(const unsigned char *lp, const unsigned char *wp, int si, float &x,
+                                                        float &y, float &aw) {
+  if constexpr (sizeof(T) == 2) {
+    const float2 xy = unpack2<T>(reinterpret_cast<const unsigned *>(lp)[si]);
+    x = xy.x;
+    y = xy.y;
+    aw = unpack2<T>((unsigned)reinterpret_cast<const unsigned short *>(wp)[si]).x;
+  } else {
+    const float2 xy = reinterpret_cast<const float2 *>(lp)[si];
+    x = xy.x;
+    y = xy.y;
+    aw = reinterpret_cast<const float *>(wp)[si];
+  }
+}
+
 // two fp32 weights -> packed 16-bit pair in the element type (low half = first)
 template <typename T>
 __device__ __forceinline__ unsigned pack_weights(float a, float b);
@@ -584,6 +603,27 @@ __device__ __forceinline__ int tile_query(const MsdaParams &p, const TileSetup &
   return (y < ts.lv[l].H && x < ts.lv[l].W) ? ts.lv[l].qstart + y * ts.lv[l].W + x : -1;
 }
 
+// First query and number of valid queries among the `qpp` consecutive tile slots [tq0, tq0 + qpp) of
+// tile t.  Requires qpp to divide the tile width, so the slots lie in one tile row and the queries are
+// consecutive in memory.
+__device__ __forceinline__ void pass_query_range(const MsdaParams &p, const TileSetup &ts, int t, int tq0, int qpp, int &q0,
+                                                 int &nq) {
+  if (!ts.tiled) {
+    q0 = (t << (p.tile_w_log2 + p.tile_h_log2)) + tq0;
+    nq = p.Q - q0;
+  } else {
+    int l = 0;
+    while (l + 1 < p.L && t >= ts.tile_first[l + 1]) ++l;
+    int tcol;
+    const int trow = fast_div(t - ts.tile_first[l], ts.tiles_x[l], ts.inv_tiles_x[l], tcol);
+    const int y = (trow << p.tile_h_log2) + (tq0 >> p.tile_w_log2);
+    const int x = (tcol << p.tile_w_log2) + (tq0 & ((1 << p.tile_w_log2) - 1));
+    q0 = ts.lv[l].qstart + y * ts.lv[l].W + x;
+    nq = (y < ts.lv[l].H) ? ts.lv[l].W - x : 0;
+  }
+  nq = nq < 0 ? 0 : (nq > qpp ? qpp : nq);
+}
+
 // ---------------------------------------------------------------------------
 // Vector kernel.
 //   T     element type (float / __half / __nv_bfloat16)
@@ -594,7 +634,7 @@ __device__ __forceinline__ int tile_query(const MsdaParams &p, const TileSetup &
 //         (small-Q / decoder shapes, to expose more parallelism)
 //   MATH  kExact: fp32 weights ; kFhfma: 16-bit weights + FHFMA
 // ---------------------------------------------------------------------------
-template <typename T, int D, int P_T, int SPLIT, int MATH>
+template <typename T, int D, int P_T, int SPLIT, int MATH, bool STAGE>
 __global__ void __launch_bounds__(kThreads, MSDA_MINB) msda_fwd_vec(const MsdaParams p) {
   constexpr int E = (int)sizeof(T);
   constexpr int VEC = 16 / E;            // channels per lane
@@ -606,7 +646,16 @@ __global__ void __launch_bounds__(kThreads, MSDA_MINB) msda_fwd_vec(const MsdaPa
   static_assert(D % VEC == 0 && GS <= 32 && (GS & (GS - 1)) == 0, "unsupported D / SPLIT");
 
   __shared__ TileSetup ts;
+  __shared__ __align__(8) uint64_t stage_bar[2];
+  extern __shared__ __align__(128) unsigned char stage_mem[];  // STAGE: 2 x (qpp loc rows + qpp weight rows)
   if (threadIdx.x < 32) setup_tiles(p, ts);
+  if constexpr (STAGE) {
+    if (threadIdx.x == 32) {
+      mbar_init(&stage_bar[0], 1);
+      mbar_init(&stage_bar[1], 1);
+      fence_mbar_init();
+    }
+  }
   __syncthreads();
 
   const char *__restrict__ value = static_cast<const char *>(p.value);
@@ -627,23 +676,77 @@ __global__ void __launch_bounds__(kThreads, MSDA_MINB) msda_fwd_vec(const MsdaPa
   const int total = ts.n_tiles * p.passes;
   const int b = blockIdx.y;
 
-  for (int w = blockIdx.x; w < total; w += gridDim.x) {
+  // When a pass is a whole number of queries (qpp > 0) the slot -> (query-in-pass, head) map does not
+  // depend on the pass and is worked out once.
+  const int ls = (int)(threadIdx.x / GS);
+  int tql = 0, m_fixed = 0;
+  if (p.qpp) {
+    if (p.head_major) {
+      const int g = ls & (PPW - 1);
+      const int qb = fast_div(ls / PPW, M, p.inv_M, m_fixed);
+      tql = qb * PPW + g;
+    } else {
+      tql = fast_div(ls, M, p.inv_M, m_fixed);
+    }
+  }
+
+  // STAGE: the locations / weights of the pass's queries are copied into shared memory by 1-D TMA bulk
+  // copies (one padded row per query, so the lane groups of a warp read distinct banks), double
+  // buffered: the copies of pass i+1 are in flight while pass i is computed.
+  const int stage_buf_bytes = p.qpp * (p.stage_loc_row + p.stage_w_row);
+  auto stage_issue = [&](int w_next, int buf) {
+    int pass;
+    const int t = fast_div(w_next, p.passes, p.inv_passes, pass);
+    int q0, nq;
+    pass_query_range(p, ts, t, pass * p.qpp, p.qpp, q0, nq);
+    const unsigned loc_bytes = (unsigned)(M * LP * 2 * E), w_bytes = (unsigned)(M * LP * E);
+    mbar_expect_tx(&stage_bar[buf], (unsigned)nq * (loc_bytes + w_bytes));
+    unsigned char *dl = stage_mem + buf * stage_buf_bytes;
+    unsigned char *dw = dl + p.qpp * p.stage_loc_row;
+    const char *gl = reinterpret_cast<const char *>(loc) + ((size_t)b * p.Q + q0) * loc_bytes;
+    const char *gw = reinterpret_cast<const char *>(wgt) + ((size_t)b * p.Q + q0) * w_bytes;
+    for (int i = 0; i < nq; ++i) {
+      tma_bulk_g2s(dl + i * p.stage_loc_row, gl + (size_t)i * loc_bytes, loc_bytes, &stage_bar[buf]);
+      tma_bulk_g2s(dw + i * p.stage_w_row, gw + (size_t)i * w_bytes, w_bytes, &stage_bar[buf]);
+    }
+  };
+  if constexpr (STAGE) {
+    if (threadIdx.x == 0 && (int)blockIdx.x < total) stage_issue(blockIdx.x, 0);
+  }
+
+  int it = 0;
+  for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
     int q, m;
     {
       int pass;
       const int t = fast_div(w, p.passes, p.inv_passes, pass);
-      const int s = pass * PAIRS_PER_PASS + (int)(threadIdx.x / GS);
       int tq;
-      if (p.head_major) {
-        // slots ordered [query block of PPW][head][query in block]: a warp holds one head of PPW
-        // neighbouring queries
-        const int g = s & (PPW - 1);
-        const int qb = fast_div(s / PPW, M, p.inv_M, m);
-        tq = qb * PPW + g;
+      if (p.qpp) {
+        tq = pass * p.qpp + tql;
+        m = m_fixed;
+        q = tile_query(p, ts, t, tq);
       } else {
-        tq = fast_div(s, M, p.inv_M, m);
+        const int s = pass * PAIRS_PER_PASS + ls;
+        if (p.head_major) {
+          // slots ordered [query block of PPW][head][query in block]: a warp holds one head of PPW
+          // neighbouring queries
+          const int g = s & (PPW - 1);
+          const int qb = fast_div(s / PPW, M, p.inv_M, m);
+          tq = qb * PPW + g;
+        } else {
+          tq = fast_div(s, M, p.inv_M, m);
+        }
+        q = (s < slots) ? tile_query(p, ts, t, tq) : -1;
       }
-      q = (s < slots) ? tile_query(p, ts, t, tq) : -1;
+    }
+    const unsigned char *slp = nullptr, *swp = nullptr;
+    if constexpr (STAGE) {
+      const int buf = it & 1;
+      __syncthreads();  // every thread has finished reading buffer buf^1 (previous pass)
+      if (threadIdx.x == 0 && w + (int)gridDim.x < total) stage_issue(w + gridDim.x, buf ^ 1);
+      mbar_wait(&stage_bar[buf], (unsigned)((it >> 1) & 1));
+      slp = stage_mem + buf * stage_buf_bytes + tql * p.stage_loc_row + m * (LP * 2 * E);
+      swp = stage_mem + buf * stage_buf_bytes + p.qpp * p.stage_loc_row + tql * p.stage_w_row + m * (LP * E);
     }
     // Padding slots (tile edge, tail of the last pass) stay in the loop with all their weights forced
     // to zero instead of branching out: the warp stays converged, so the shuffles below can name all 32
@@ -670,11 +773,15 @@ __global__ void __launch_bounds__(kThreads, MSDA_MINB) msda_fwd_vec(const MsdaPa
         constexpr unsigned group_mask = 0xffffffffu;
         const int ks = sub & 3;
         float nx, ny, naw;
-        load_sample_inputs<T>(lp, wp, ks, nx, ny, naw);
+        if constexpr (STAGE) load_sample_inputs_smem<T>(slp, swp, ks, nx, ny, naw);
+        else load_sample_inputs<T>(lp, wp, ks, nx, ny, naw);
         for (int l = 0; l < p.L; ++l) {
           const int H = ts.lv[l].H, W = ts.lv[l].W;
           const float x = nx, y = ny, aw = live ? naw : 0.f;
-          if (l + 1 < p.L) load_sample_inputs<T>(lp, wp, (l + 1) * 4 + ks, nx, ny, naw);  // prefetch next level
+          if (l + 1 < p.L) {  // prefetch next level
+            if constexpr (STAGE) load_sample_inputs_smem<T>(slp, swp, (l + 1) * 4 + ks, nx, ny, naw);
+            else load_sample_inputs<T>(lp, wp, (l + 1) * 4 + ks, nx, ny, naw);
+          }
           int i00;
           float cw[4];
           make_geo(x, y, aw, H, W, i00, cw);
@@ -845,11 +952,20 @@ struct VecPlan {
   int split;
   int math;
   unsigned grid, grid_y;
+  unsigned stage_bytes;  // dynamic shared memory of the TMA staging buffers, 0 = direct loads
 };
 
 template <typename T, int D, int P_T, int SPLIT, int MATH>
 int launch_vec_inst(const MsdaParams &p, const VecPlan &plan, cudaStream_t stream) {
-  msda_fwd_vec<T, D, P_T, SPLIT, MATH><<<dim3(plan.grid, plan.grid_y, 1), kThreads, 0, stream>>>(p);
+  constexpr int G = D * (int)sizeof(T) / 16;
+  if constexpr (P_T == 4 && SPLIT == 1 && G >= 4) {
+    if (plan.stage_bytes > 0) {
+      msda_fwd_vec<T, D, P_T, SPLIT, MATH, true><<<dim3(plan.grid, plan.grid_y, 1), kThreads, plan.stage_bytes, stream>>>(p);
+      g_launch_count.fetch_add(1, std::memory_order_relaxed);
+      return (int)cudaGetLastError();
+    }
+  }
+  msda_fwd_vec<T, D, P_T, SPLIT, MATH, false><<<dim3(plan.grid, plan.grid_y, 1), kThreads, 0, stream>>>(p);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return (int)cudaGetLastError();
 }
@@ -928,11 +1044,15 @@ int forward_impl(MsdaParams p, int dtype, unsigned flags, cudaStream_t stream) {
   plan.split = env_int("MSDA_B200_SPLIT", plan.split);
   if (plan.split != 4 || G * 4 > 32) plan.split = 1;
 
-  plan.math = kExact;
+  // fp16 defaults to the FHFMA path (combined weights rounded to fp16: measured max-normalised error
+  // 4.7e-4 vs 2.7e-4 for fp32 weights at the headline shape, gate 2e-3); bf16 weights would keep only 8
+  // bits, so bf16 defaults to fp32 weights
+  plan.math = (dtype == MSDA_F16) ? kFhfma : kExact;
   if (E == 2) {
     if (flags & MSDA_FLAG_MATH_FHFMA) plan.math = kFhfma;
     if (flags & MSDA_FLAG_MATH_EXACT) plan.math = kExact;
   }
+  if (E != 2) plan.math = kExact;
 
   const int ppw = 32 / (G * plan.split);
   const int pairs_per_pass = kThreads / (G * plan.split);
@@ -957,6 +1077,31 @@ int forward_impl(MsdaParams p, int dtype, unsigned flags, cudaStream_t stream) {
   p.passes = (int)passes;
   p.inv_passes = 1.0f / (float)passes;
   p.inv_M = 1.0f / (float)p.M;
+  // a pass is a whole number of queries when M divides the pairs per pass (and, head-major, the block
+  // of ppw queries divides it too); then it also divides the power-of-two tile width
+  p.qpp = 0;
+  if (pairs_per_pass % p.M == 0) {
+    const int qpp = pairs_per_pass / p.M;
+    if ((qpp & (qpp - 1)) == 0 && qpp % ppw == 0 && qpp <= (1 << p.tile_w_log2)) p.qpp = qpp;
+  }
+  // TMA staging of locations / weights: P == 4 broadcast path, whole-query passes, 16-byte aligned rows
+  plan.stage_bytes = 0;
+  p.stage_loc_row = p.stage_w_row = 0;
+  const bool want_stage = ((flags & MSDA_FLAG_STAGE_TMA) || env_int("MSDA_B200_STAGE", 0)) && !(flags & MSDA_FLAG_NO_STAGING);
+  if (p.qpp > 0 && p.P == 4 && plan.split == 1 && G >= 4 && want_stage) {
+    const size_t loc_row = (size_t)p.M * p.L * p.P * 2 * E, w_row = (size_t)p.M * p.L * p.P * E;
+    auto pad_row = [](size_t bytes) {  // row pitch = 4 (mod 8) words: the 8 lane groups of a warp hit distinct banks
+      size_t r = bytes;
+      while ((r / 4) % 8 != 4) r += 16;
+      return r;
+    };
+    if (loc_row % 16 == 0 && w_row % 16 == 0 && aligned_to(p.loc, 16) && aligned_to(p.weight, 16)) {
+      p.stage_loc_row = (int)pad_row(loc_row);
+      p.stage_w_row = (int)pad_row(w_row);
+      const size_t total = 2 * (size_t)p.qpp * (p.stage_loc_row + p.stage_w_row);
+      if (total <= 40 * 1024) plan.stage_bytes = (unsigned)total;
+    }
+  }
 
   // grid: x strides over the (tile, pass) units of one image, y = image.  The level shapes are
   // device-resident, so the exact 2-D tile count is unknown here; the kernel strides over the real
@@ -983,9 +1128,10 @@ int forward_impl(MsdaParams p, int dtype, unsigned flags, cudaStream_t stream) {
     default: return MSDA_ERR_BAD_DTYPE;
   }
   if (rc == 0) {
-    snprintf(g_last_variant, sizeof(g_last_variant), "vec<%s,D%d,P%d,split%d>/%s%dx%d/%s/%s", dtype_name(dtype), p.D,
+    snprintf(g_last_variant, sizeof(g_last_variant), "vec<%s,D%d,P%d,split%d>/%s%dx%d/%s/%s%s", dtype_name(dtype), p.D,
              p.P == 4 ? 4 : 0, plan.split, p.want_tiled ? "tiled" : "linear", 1 << p.tile_w_log2, 1 << p.tile_h_log2,
-             p.head_major ? "head-major" : "query-major", plan.math == kFhfma ? "fhfma" : "exact");
+             p.head_major ? "head-major" : "query-major", plan.math == kFhfma ? "fhfma" : "exact",
+             plan.stage_bytes ? "/tma-staged" : "");
   }
   return rc;
 }

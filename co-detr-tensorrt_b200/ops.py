@@ -285,6 +285,28 @@ class HostForward:
         return int(h2d), int(d2h)
 
 
+def read_bandwidth_probe(device: torch.device, working_set_bytes: int, repeats: int, trials: int = 3) -> float:
+    """GB/s of 16-byte streaming reads over a working set (``msda_b200_read_probe``): a set well below
+    the 126 MB L2 measures L2->SM bandwidth, one far above it HBM.  Used for the roofline denominators
+    MEASURED_PEAKS.json does not carry."""
+    with torch.cuda.device(device):
+        buf = torch.empty(int(working_set_bytes), dtype=torch.uint8, device=device).random_(0, 255)
+        sink = torch.zeros(4, dtype=torch.int32, device=device)
+        stream = torch.cuda.current_stream(device).cuda_stream
+        for _ in range(2):
+            _check(_lib.msda_b200_read_probe(buf.data_ptr(), buf.numel(), repeats, sink.data_ptr(), stream))
+        torch.cuda.synchronize(device)
+        best = 0.0
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(trials):
+            start.record()
+            _check(_lib.msda_b200_read_probe(buf.data_ptr(), buf.numel(), repeats, sink.data_ptr(), stream))
+            end.record()
+            torch.cuda.synchronize(device)
+            best = max(best, buf.numel() * repeats / (start.elapsed_time(end) * 1e-3) / 1e9)
+    return best
+
+
 # ---------------------------------------------------------------------------
 # torch.library registration: same namespace, name and schema as the reference
 # ---------------------------------------------------------------------------

@@ -67,9 +67,12 @@ enum msda_flags {
   MSDA_FLAG_DEFAULT = 0,
   MSDA_FLAG_FORCE_GENERIC = 1 << 0, /* use the shape-agnostic scalar kernel               */
   MSDA_FLAG_LINEAR_ORDER = 1 << 1,  /* do not re-tile queries spatially (encoder shapes)  */
-  MSDA_FLAG_MATH_FHFMA = 1 << 2,    /* fp16/bf16: Blackwell FHFMA with 16-bit weights     */
+  MSDA_FLAG_MATH_FHFMA = 1 << 2,    /* fp16/bf16: Blackwell FHFMA, combined weights rounded to the 16-bit type
+                                       (default for fp16; bf16 defaults to exact)         */
   MSDA_FLAG_MATH_EXACT = 1 << 3,    /* fp16/bf16: fp32 weights, convert + FFMA            */
-  MSDA_FLAG_NO_STAGING = 1 << 4     /* do not stage loc/weights through shared memory     */
+  MSDA_FLAG_NO_STAGING = 1 << 4,    /* never stage loc/weights through shared memory (the default) */
+  MSDA_FLAG_STAGE_TMA = 1 << 5      /* stage loc/weights of each pass with TMA bulk copies (opt-in:
+                                       measured slightly slower than direct loads) */
 };
 
 /*

@@ -121,6 +121,8 @@ def main():
         {"name": "query-major", "flags": 0, "MSDA_B200_HEAD_MAJOR": 0},
         {"name": "query-major+linear", "flags": cb.FLAG_LINEAR_ORDER, "MSDA_B200_HEAD_MAJOR": 0},
         {"name": "generic", "flags": cb.FLAG_FORCE_GENERIC},
+        {"name": "nostage", "flags": cb.FLAG_NO_STAGING},
+        {"name": "fhfma+nostage", "flags": cb.FLAG_MATH_FHFMA | cb.FLAG_NO_STAGING},
     ]
     tile_cfgs = [{"name": f"tile{w}x{h}+fhfma", "flags": cb.FLAG_MATH_FHFMA, "MSDA_B200_TILE_W": w, "MSDA_B200_TILE_H": h}
                  for (w, h) in ((8, 1), (8, 2), (8, 8), (16, 2), (16, 4), (4, 4), (32, 2), (32, 8))]
@@ -143,8 +145,13 @@ def main():
             cfgs = [c for c in cfgs if "fhfma" not in c["name"]]
         if args.only == "headline":
             cfgs = [c for c in cfgs if c["name"] in ("default", "fhfma", "linear+fhfma", "query-major", "tile8x8+fhfma", "tile16x4+fhfma",
-                                                      "tile4x4+fhfma", "split1", "split4", "split1+fhfma")]
+                                                      "tile4x4+fhfma", "split1", "split4", "split1+fhfma", "nostage", "fhfma+nostage")]
             have_ref = False
+        ref32 = None
+        if dtn != "float32":
+            s0 = sets[0]
+            ref32 = cb.multi_scale_deformable_attention(s0["value"].float(), s0["spatial_shapes"], s0["level_start_index"],
+                                                        s0["sampling_loc"].float(), s0["attn_weight"].float(), flags=0)
         for cfg in cfgs:
             set_env(cfg)
             calls = [cb.PreparedForward(*(s[k] for k in KEYS), flags=cfg["flags"]) for s in sets]
@@ -152,9 +159,13 @@ def main():
             row = {"workload": name, "batch": batch, "dtype": dtn, "loc_mode": loc_mode or wl.kind, "config": cfg["name"],
                    "variant": cb.last_variant(), "us_per_call": us, "hbm_GBps": hbm / us / 1e3, "gather_GBps": gather / us / 1e3,
                    "images_per_s": batch / (us * 1e-6), "n_sets": len(sets)}
+            if ref32 is not None:
+                got = calls[0]().float()
+                torch.cuda.synchronize()
+                row["max_rel_vs_fp32"] = float((got - ref32).abs().max() / ref32.abs().max())
             results["rows"].append(row)
             print(f"{name:24s} b{batch} {dtn:8s} {row['loc_mode']:8s} {cfg['name']:20s} {us:9.2f} us  hbm {row['hbm_GBps']:7.1f} GB/s  "
-                  f"gather {row['gather_GBps']:8.1f} GB/s   {row['variant']}", flush=True)
+                  f"gather {row['gather_GBps']:8.1f} GB/s  err {row.get('max_rel_vs_fp32', 0):.2e}  {row['variant']}", flush=True)
         set_env({})
         if have_ref and dtn in ("float16", "float32"):
             fns = [(lambda s=s: torch.ops.codetr_ref.multi_scale_deformable_attention(*(s[k] for k in KEYS), 64)) for s in sets]

@@ -29,6 +29,8 @@ FLAG_SETS = {
     "linear": cb.FLAG_LINEAR_ORDER,
     "fhfma": cb.FLAG_MATH_FHFMA,
     "exact": cb.FLAG_MATH_EXACT,
+    "staged": cb.FLAG_STAGE_TMA,
+    "staged+fhfma": cb.FLAG_STAGE_TMA | cb.FLAG_MATH_FHFMA,
 }
 
 
@@ -64,7 +66,7 @@ def ref32_of(d):
 # ----------------------------------------------------------------------------------------------
 # golden vectors
 # ----------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("flagset", ["default", "generic", "linear"])
+@pytest.mark.parametrize("flagset", ["default", "generic", "linear", "staged"])
 @pytest.mark.parametrize("case", CASES, ids=[c.name for c in CASES])
 def test_fp32_matches_golden(case, flagset, cuda_device):
     arrs, z = load_case(case)
@@ -82,7 +84,7 @@ def test_fp64_matches_golden(case, cuda_device):
     assert max_rel(out.cpu().numpy(), z["out_f64"]) < 1e-13
 
 
-@pytest.mark.parametrize("flagset", ["default", "generic", "linear", "fhfma", "exact"])
+@pytest.mark.parametrize("flagset", ["default", "generic", "linear", "fhfma", "exact", "staged", "staged+fhfma"])
 @pytest.mark.parametrize("dt", ["f16", "bf16"])
 @pytest.mark.parametrize("case", CASES, ids=[c.name for c in CASES])
 def test_half_matches_fp32_reference(case, dt, flagset, cuda_device):
@@ -94,7 +96,7 @@ def test_half_matches_fp32_reference(case, dt, flagset, cuda_device):
     err = max_rel(got, ref)
     if dt == "f16":
         assert err <= HALF_MAX_REL, f"{case.name} {dt} {flagset}: {err:.3e}"
-    elif flagset != "fhfma":
+    elif "fhfma" not in flagset:
         # bf16: one output rounding (see parity.BF16_MAX_REL) -- fp32 arithmetic inside, so every element
         # is the correctly rounded bf16 value or its neighbour
         assert err <= BF16_MAX_REL, f"{case.name} {dt} {flagset}: {err:.3e}"
@@ -353,9 +355,17 @@ def test_full_size_configs_against_oracle(name, dt, cuda_device):
         assert rel_l2(out.cpu().numpy(), ref) <= FP32_REL_L2
     else:
         assert max_rel(out.float().cpu().numpy(), ref) <= (HALF_MAX_REL if dt == "f16" else BF16_MAX_REL)
-    # schedule independence: linear query order gives the same bits
+    # schedule independence: linear query order and TMA-staged inputs give the same bits
     lin = cb.multi_scale_deformable_attention(*(d[k] for k in ARRAY_KEYS), flags=cb.FLAG_LINEAR_ORDER)
     assert torch.equal(out, lin)
+    staged = cb.multi_scale_deformable_attention(*(d[k] for k in ARRAY_KEYS), flags=cb.FLAG_STAGE_TMA)
+    assert torch.equal(out, staged)
+    if dt != "f32":
+        # both 16-bit math modes meet the gate at full size
+        for fl in (cb.FLAG_MATH_EXACT, cb.FLAG_MATH_FHFMA):
+            alt = cb.multi_scale_deformable_attention(*(d[k] for k in ARRAY_KEYS), flags=fl)
+            bound = HALF_MAX_REL if dt == "f16" else (BF16_MAX_REL if fl == cb.FLAG_MATH_EXACT else 3 * BF16_MAX_REL)
+            assert max_rel(alt.float().cpu().numpy(), ref) <= bound
 
 
 @pytest.mark.parametrize("loc_mode", ["uniform", "encoder"])
