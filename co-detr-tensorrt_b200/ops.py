@@ -285,6 +285,69 @@ class HostForward:
         return int(h2d), int(d2h)
 
 
+class HostPipeline:
+    """Software-pipelined end-to-end calls for HOST buffers: ``depth`` slots, each with its own stream,
+    device workspace and pinned output, so the host->device copy of call i+1, the kernel of call i and the
+    device->host copy of call i-1 overlap (PCIe is full duplex and the copy engines run beside the SMs).
+    Every call still moves all of its inputs and its result across PCIe through
+    ``msda_b200_forward_host``.
+
+        pipe = HostPipeline(device)
+        t = pipe.submit(value, shapes, starts, loc, weight)     # returns immediately
+        out = pipe.result(t)                                     # pinned host tensor, synchronised
+    """
+
+    def __init__(self, device: torch.device, depth: int = 3):
+        self.device = torch.device(device)
+        self.depth = int(depth)
+        with torch.cuda.device(self.device):
+            self._streams = [torch.cuda.Stream(device=self.device) for _ in range(self.depth)]
+        self._events = [None] * self.depth
+        self._ws = [None] * self.depth
+        self._out = [None] * self.depth
+        self._next = 0
+
+    def submit(self, value: Tensor, spatial_shapes: Tensor, level_start_index: Tensor, sampling_loc: Tensor,
+               attn_weight: Tensor, im2col_step: int = 64, flags: Optional[int] = None) -> int:
+        for t in (value, spatial_shapes, level_start_index, sampling_loc, attn_weight):
+            _require(not t.is_cuda and t.is_contiguous(), "HostPipeline takes contiguous host tensors")
+        slot = self._next
+        self._next = (self._next + 1) % self.depth
+        if self._events[slot] is not None:
+            self._events[slot].synchronize()  # the slot's previous call (and its output copy) has finished
+        bs, keys, heads, chans = value.shape
+        queries, levels, points = sampling_loc.shape[1], sampling_loc.shape[3], sampling_loc.shape[4]
+        dt = _DTYPES[value.dtype]
+        need = int(_lib.msda_b200_host_workspace_bytes(bs, keys, heads, chans, levels, queries, points, dt))
+        with torch.cuda.device(self.device):
+            if self._ws[slot] is None or self._ws[slot].numel() < need:
+                self._ws[slot] = torch.empty(max(need, 256), dtype=torch.uint8, device=self.device)
+            shape = (bs, queries, heads * chans)
+            if self._out[slot] is None or tuple(self._out[slot].shape) != shape or self._out[slot].dtype != value.dtype:
+                self._out[slot] = torch.empty(shape, dtype=value.dtype).pin_memory()
+            stream = self._streams[slot]
+            rc = _lib.msda_b200_forward_host(
+                value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), sampling_loc.data_ptr(),
+                attn_weight.data_ptr(), self._out[slot].data_ptr(), self._ws[slot].data_ptr(), self._ws[slot].numel(),
+                bs, keys, heads, chans, levels, queries, points, int(im2col_step), dt,
+                _default_flags if flags is None else int(flags), int(stream.cuda_stream),
+            )
+            _check(rc)
+            ev = torch.cuda.Event()
+            ev.record(stream)
+            self._events[slot] = ev
+        return slot
+
+    def result(self, ticket: int) -> Tensor:
+        self._events[ticket].synchronize()
+        return self._out[ticket]
+
+    def drain(self) -> None:
+        for ev in self._events:
+            if ev is not None:
+                ev.synchronize()
+
+
 def read_bandwidth_probe(device: torch.device, working_set_bytes: int, repeats: int, trials: int = 3) -> float:
     """GB/s of 16-byte streaming reads over a working set (``msda_b200_read_probe``): a set well below
     the 126 MB L2 measures L2->SM bandwidth, one far above it HBM.  Used for the roofline denominators

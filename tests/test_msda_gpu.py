@@ -339,13 +339,26 @@ def test_fused_producers(kind, q, dtype, cuda_device):
 FULL = ["r50_enc_608", "swinl_enc_1152x768", "swinl_dec_1152x768", "swinl_enc_1920x1280", "swinl_dec_1900q"]
 
 
+_FULL_INPUTS = {}
+
+
+def _full_inputs(name, batch):
+    """Full-size synthetic inputs, generated once per (workload, batch) for the whole session."""
+    key = (name, batch)
+    if key not in _FULL_INPUTS:
+        if len(_FULL_INPUTS) > 3:
+            _FULL_INPUTS.clear()
+        inp = W.make_inputs(W.CONFIGS[name], batch=batch)
+        _FULL_INPUTS[key] = {k: getattr(inp, k) for k in ARRAY_KEYS}
+    return _FULL_INPUTS[key]
+
+
 @pytest.mark.parametrize("dt", ["f16", "bf16", "f32"])
 @pytest.mark.parametrize("name", FULL)
 def test_full_size_configs_against_oracle(name, dt, cuda_device):
     wl = W.CONFIGS[name]
-    batch = 1 if dt == "f32" else wl.batch
-    inp = W.make_inputs(wl, batch=batch)
-    arrs = {k: getattr(inp, k) for k in ARRAY_KEYS}
+    batch = 1
+    arrs = _full_inputs(name, batch)
     before = cb.launch_count()
     out, d = run_op(arrs, TORCH_DT[dt], cuda_device)
     assert cb.launch_count() == before + 1          # one kernel per call, whatever the batch
@@ -392,3 +405,33 @@ def test_full_size_properties(loc_mode, cuda_device):
     ones = cb.multi_scale_deformable_attention(torch.full_like(v1, 3.0), d["spatial_shapes"], d["level_start_index"], loc,
                                                d["attn_weight"])
     assert (ones - 3.0).abs().max().item() < 1e-4
+
+
+def test_config5_plugin_path_batch2(cuda_device):
+    """BASELINE configs[4]: Swin-L encoder at 1920x1280 (S=Q=51,150), two images per GPU, launched the way
+    TensorRT's enqueue launches it: raw pointers, device int64 shapes, external stream, un-zeroed output."""
+    wl = W.CONFIGS["swinl_enc_1920x1280"]
+    inp = W.make_inputs(wl, batch=2)
+    d = to_dev({k: getattr(inp, k) for k in ARRAY_KEYS}, torch.float16, cuda_device)
+    out = torch.full((2, wl.Q, 256), float("nan"), dtype=torch.float16, device=cuda_device)
+    stream = torch.cuda.Stream(device=cuda_device)
+    stream.wait_stream(torch.cuda.current_stream(cuda_device))
+    rc = cb.plugin_enqueue(d["value"].shape, d["sampling_loc"].shape, cb.ops.TRT_HALF, [d[k].data_ptr() for k in ARRAY_KEYS],
+                           out.data_ptr(), stream.cuda_stream)
+    assert rc == 0
+    stream.synchronize()
+    assert max_rel(out.float().cpu().numpy(), ref32_of(d)) <= HALF_MAX_REL
+
+
+def test_host_pipeline_matches_synchronous_calls(cuda_device):
+    _, inp = _small(cuda_device)
+    host = {k: torch.from_numpy(getattr(inp, k)).pin_memory() for k in ARRAY_KEYS}
+    want = cb.HostForward(cuda_device)(*(host[k] for k in ARRAY_KEYS)).clone()
+    pipe = cb.HostPipeline(cuda_device, depth=3)
+    tickets = [pipe.submit(*(host[k] for k in ARRAY_KEYS)) for _ in range(3)]
+    for t in tickets:
+        assert torch.equal(pipe.result(t), want)
+    for _ in range(7):  # slots are reused safely
+        t = pipe.submit(*(host[k] for k in ARRAY_KEYS))
+    pipe.drain()
+    assert torch.equal(pipe.result(t), want)
