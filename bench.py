@@ -50,6 +50,7 @@ def parse_args():
     ap.add_argument("--dtype", default=None, choices=[None, "float16", "bfloat16", "float32"])
     ap.add_argument("--loc-mode", default=None, choices=[None, "encoder", "decoder", "uniform"])
     ap.add_argument("--flags", type=int, default=None, help="msda_flags bit field (default: library default)")
+    ap.add_argument("--workspace", action="store_true", help="give the library a scratch buffer (packed-pyramid path)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cuda-graph", action="store_true", help="replay the K steps from one captured CUDA graph")
@@ -270,7 +271,11 @@ def run_b200(args):
     for i in range(n_sets):
         hs = host_sets[i % 2]
         d = {k: hs[k].to(dev, non_blocking=True) for k in keys}
-        calls.append(cb.PreparedForward(*(d[k] for k in keys), flags=args.flags))
+        ws = None
+        if args.workspace:
+            need = cb.workspace_bytes(d["value"], d["sampling_loc"])
+            ws = torch.empty(need, dtype=torch.uint8, device=dev) if need else None
+        calls.append(cb.PreparedForward(*(d[k] for k in keys), flags=args.flags, workspace=ws))
     torch.cuda.synchronize()
 
     def barrier():

@@ -34,6 +34,9 @@ NVCC_FLAGS = [
 # every symbol include/msda_b200.h declares
 EXPORTED_SYMBOLS = [
     "msda_b200_forward",
+    "msda_b200_forward_ws",
+    "msda_b200_workspace_bytes",
+    "msda_b200_plugin_workspace_bytes",
     "msda_b200_plugin_enqueue",
     "msda_b200_forward_fused",
     "msda_b200_host_workspace_bytes",
@@ -54,6 +57,8 @@ FLAG_MATH_FHFMA = 1 << 2
 FLAG_MATH_EXACT = 1 << 3
 FLAG_NO_STAGING = 1 << 4
 FLAG_STAGE_TMA = 1 << 5
+FLAG_NO_PACKED = 1 << 6
+FLAG_HEAD_MAJOR = 1 << 7
 
 
 class NativeLibraryError(RuntimeError):
@@ -119,8 +124,15 @@ def load() -> ctypes.CDLL:
     lib.msda_b200_forward.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, i64, i64, i64, ci, cu, vp]
     lib.msda_b200_forward_fused.restype = ci
     lib.msda_b200_forward_fused.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, i64, i64, i64, ci, cu, vp]
+    lib.msda_b200_forward_ws.restype = ci
+    lib.msda_b200_forward_ws.argtypes = [vp, vp, vp, vp, vp, vp, vp, ctypes.c_size_t,
+                                         i64, i64, i64, i64, i64, i64, i64, i64, ci, cu, vp]
+    lib.msda_b200_workspace_bytes.restype = ctypes.c_size_t
+    lib.msda_b200_workspace_bytes.argtypes = [i64, i64, i64, i64, i64, i64, i64, ci]
+    lib.msda_b200_plugin_workspace_bytes.restype = ctypes.c_size_t
+    lib.msda_b200_plugin_workspace_bytes.argtypes = [vp, vp, ci]
     lib.msda_b200_plugin_enqueue.restype = ci
-    lib.msda_b200_plugin_enqueue.argtypes = [vp, vp, ci, vp, vp, vp, i64, vp]
+    lib.msda_b200_plugin_enqueue.argtypes = [vp, vp, ci, vp, vp, vp, ctypes.c_size_t, i64, vp]
     lib.msda_b200_host_workspace_bytes.restype = ctypes.c_size_t
     lib.msda_b200_host_workspace_bytes.argtypes = [i64, i64, i64, i64, i64, i64, i64, ci]
     lib.msda_b200_forward_host.restype = ci

@@ -62,6 +62,13 @@ constexpr int kThreads = 256;
 #ifndef MSDA_NB
 #define MSDA_NB 1
 #endif
+#ifndef MSDA_LB
+#define MSDA_LB 1   // levels whose row loads are issued together in the split-points path (measured: 1 is best,
+                    // more registers per thread push the 450-CTA decoder grid into a second wave)
+#endif
+#ifndef MSDA_MINB_SPLIT
+#define MSDA_MINB_SPLIT 4
+#endif
 
 std::atomic<uint64_t> g_launch_count{0};
 thread_local char g_last_variant[128] = "none";
@@ -110,6 +117,7 @@ struct MsdaParams {
   const void *offsets;    // [B,Q,M,L,P,2]            (fused mode)
   const void *logits;     // [B,Q,M,L*P]              (fused mode)
   void *out;              // [B,Q,M*D]
+  void *packed;           // workspace: pixel-pair packed value pyramid (packed path), else nullptr
   int B, S, M, D, L, Q, P;
   int ref_dim;  // 0 = plain mode, 2 or 4 = fused mode
   int tile_w_log2, tile_h_log2;  // query tile is 2^tile_w_log2 x 2^tile_h_log2 (tiled) or that many consecutive queries (linear)
@@ -537,6 +545,7 @@ struct TileSetup {
   float inv_tiles_x[kMaxLevelsSmem];
   int n_tiles;                         // tiles per image
   int tiled;                           // 1 = 2-D tiles, 0 = linear chunks
+  int layout_ok;                       // 1 = levels are disjoint key ranges inside [0, S) (packed path)
 };
 
 __device__ __forceinline__ void setup_tiles(const MsdaParams &p, TileSetup &ts) {
@@ -575,7 +584,15 @@ __device__ __forceinline__ void setup_tiles(const MsdaParams &p, TileSetup &ts) 
   }
   const int q_total = __shfl_sync(0xffffffffu, qs, 31);
   const int t_total = __shfl_sync(0xffffffffu, tsum, 31);
+  // standard pyramid layout? every level a key range inside [0, S), pairwise disjoint
+  bool bad = (l < p.L) && (start < 0 || H < 0 || W < 0 || (long long)start + (long long)nq > (long long)p.S);
+  for (int o = 0; o < p.L; ++o) {
+    const int os = __shfl_sync(0xffffffffu, start, o), on = __shfl_sync(0xffffffffu, nq, o);
+    if (l < p.L && o != l && nq > 0 && on > 0 && start < os + on && os < start + nq) bad = true;
+  }
+  const unsigned any_bad = __ballot_sync(0xffffffffu, bad);
   if (l == 0) {
+    ts.layout_ok = any_bad == 0u;
     ts.tile_first[p.L] = t_total;
     const int tq_log2 = p.tile_w_log2 + p.tile_h_log2;
     if (p.want_tiled && q_total == p.Q) {
@@ -635,7 +652,7 @@ __device__ __forceinline__ void pass_query_range(const MsdaParams &p, const Tile
 //   MATH  kExact: fp32 weights ; kFhfma: 16-bit weights + FHFMA
 // ---------------------------------------------------------------------------
 template <typename T, int D, int P_T, int SPLIT, int MATH, bool STAGE>
-__global__ void __launch_bounds__(kThreads, MSDA_MINB) msda_fwd_vec(const MsdaParams p) {
+__global__ void __launch_bounds__(kThreads, (SPLIT > 1 && P_T == 4) ? MSDA_MINB_SPLIT : MSDA_MINB) msda_fwd_vec(const MsdaParams p) {
   constexpr int E = (int)sizeof(T);
   constexpr int VEC = 16 / E;            // channels per lane
   constexpr int G = D / VEC;             // lanes per corner row
@@ -831,9 +848,58 @@ __global__ void __launch_bounds__(kThreads, MSDA_MINB) msda_fwd_vec(const MsdaPa
             }
           }
         }
+      } else if constexpr (P_T == 4) {
+        // ---- split-points path (small Q, e.g. the decoder's 900 queries): the four points of a level are
+        // dealt to SPLIT lane groups, and the row loads of LB levels are all issued before the first FMA,
+        // so one lane has LB * (4/SPLIT) * 4 independent loads in flight -- the problem is too small to
+        // hide memory latency with occupancy.
+        constexpr int SPL = 4 / SPLIT;   // samples per level per lane group
+        constexpr int LB = MSDA_LB;      // levels per batch
+        for (int l0 = 0; l0 < p.L; l0 += LB) {
+          uint4 rows[LB][SPL][4];
+          float cwb[LB][SPL][4];
+#pragma unroll
+          for (int lb = 0; lb < LB; ++lb) {
+            const int l = l0 + lb;
+#pragma unroll
+            for (int ss = 0; ss < SPL; ++ss) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) cwb[lb][ss][j] = 0.f;
+            }
+            if (l < p.L) {
+              const int H = ts.lv[l].H, W = ts.lv[l].W;
+              const char *vl = vm + (size_t)ts.lv[l].start * pix_bytes;
+#pragma unroll
+              for (int ss = 0; ss < SPL; ++ss) {
+                float x, y, aw;
+                load_sample_inputs<T>(lp, wp, l * 4 + split + ss * SPLIT, x, y, aw);
+                aw = live ? aw : 0.f;
+                int i00;
+                make_geo(x, y, aw, H, W, i00, cwb[lb][ss]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const int idx = i00 + (j & 1) + ((j & 2) ? W : 0);
+                  if (cwb[lb][ss][j] != 0.f) rows[lb][ss][j] = ldg128(vl + (size_t)(unsigned)idx * pix_bytes);
+                }
+              }
+            }
+          }
+#pragma unroll
+          for (int lb = 0; lb < LB; ++lb) {
+#pragma unroll
+            for (int ss = 0; ss < SPL; ++ss) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                if (cwb[lb][ss][j] != 0.f) {
+                  if constexpr (MATH == kFhfma) RowFma<T, kFhfma>::run(acc, rows[lb][ss][j], 0.f, weight_to_16<T>(cwb[lb][ss][j]));
+                  else RowFma<T, kExact>::run(acc, rows[lb][ss][j], cwb[lb][ss][j], 0u);
+                }
+              }
+            }
+          }
+        }
       } else {
-        // ---- run-time P, split points, or rows narrower than four lanes: every lane works out the
-        // geometry of the samples it consumes
+        // ---- run-time P: every lane works out the geometry of the samples it consumes
         for (int l = 0; l < p.L; ++l) {
           const int H = ts.lv[l].H, W = ts.lv[l].W;
           const char *vl = vm + (size_t)ts.lv[l].start * pix_bytes;
@@ -874,6 +940,231 @@ __global__ void __launch_bounds__(kThreads, MSDA_MINB) msda_fwd_vec(const MsdaPa
       }
       if (live && split == 0) store_row<T, VEC>(out + pair * D + sub * VEC, acc);
     }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Packed path (16-bit types, D = 32, P = 4): pixel-pair packed pyramid + 256-bit loads.
+//
+// In the channels-last value tensor a (pixel, head) row is 64 B, half an L1 line, so each of the four
+// bilinear corners costs a full L1 wavefront.  The pre-pass below re-lays the pyramid out so that one
+// 128-byte, line-aligned entry per (pixel, head) holds the row of the pixel AND of its right-hand
+// neighbour (zeros at the end of an image row), chunk-interleaved:
+//     entry(s, m) = [ v(s)[0:8] | v(s+1)[0:8] | v(s)[8:16] | v(s+1)[8:16] | ... ]   (4 x 32 B)
+// A lane group then fetches BOTH horizontal corners of a sample with one LDG.E.256 per lane
+// (ld.global.nc.v8.b32, sm_100+): two wavefronts per sample instead of four.
+// ---------------------------------------------------------------------------
+struct U8 {
+  unsigned v[8];
+};
+
+__device__ __forceinline__ U8 ldg256(const void *ptr) {
+  U8 r;
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+               : "l"(ptr));
+  return r;
+}
+__device__ __forceinline__ void stg256(void *ptr, const uint4 &a, const uint4 &b) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ptr), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x),
+               "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
+
+// pre-pass: one thread per (pixel, head, 16-byte chunk)
+template <typename T>
+__global__ void __launch_bounds__(kThreads) msda_pack_value(const MsdaParams p) {
+  __shared__ TileSetup ts;
+  if (threadIdx.x < 32) setup_tiles(p, ts);
+  __syncthreads();
+  if (!ts.layout_ok) return;  // exotic level layout: the main kernel takes its generic fallback
+  const char *__restrict__ value = static_cast<const char *>(p.value);
+  char *__restrict__ packed = static_cast<char *>(p.packed);
+  const int M = p.M;
+  const long long n = (long long)p.B * p.S * M * 4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(i & 3);
+    const long long pm = i >> 2;          // (b*S + s)*M + m
+    const long long bs = pm / M;
+    const int s = (int)(bs % p.S);
+    // does pixel s have a right-hand neighbour in its image row?
+    bool has_right = false;
+    for (int l = 0; l < p.L; ++l) {
+      const int rel = s - ts.lv[l].start;
+      if (rel >= 0 && rel < ts.lv[l].H * ts.lv[l].W) {
+        const int W = ts.lv[l].W;
+        has_right = (rel % W) + 1 < W;
+      }
+    }
+    const uint4 left = __ldg(reinterpret_cast<const uint4 *>(value + pm * 64 + j * 16));
+    uint4 right = make_uint4(0u, 0u, 0u, 0u);
+    if (has_right) right = __ldg(reinterpret_cast<const uint4 *>(value + (pm + M) * 64 + j * 16));
+    stg256(packed + pm * 128 + j * 32, left, right);
+  }
+}
+
+// fp32-weight FMA of one 16-byte piece (8 channels)
+template <typename T, int MATH>
+__device__ __forceinline__ void piece_fma(float (&acc)[8], const unsigned *r, float w, unsigned w16) {
+  const uint4 q = make_uint4(r[0], r[1], r[2], r[3]);
+  RowFma<T, MATH>::run(acc, q, w, w16);
+}
+
+template <typename T, int MATH>
+__global__ void __launch_bounds__(kThreads, MSDA_MINB) msda_fwd_packed(const MsdaParams p) {
+  constexpr int D = 32, E = 2, G = 4, PPW = 8, PAIRS_PER_PASS = kThreads / G;
+  __shared__ TileSetup ts;
+  if (threadIdx.x < 32) setup_tiles(p, ts);
+  __syncthreads();
+
+  const T *__restrict__ loc = static_cast<const T *>(p.loc);
+  const T *__restrict__ wgt = static_cast<const T *>(p.weight);
+  T *__restrict__ out = static_cast<T *>(p.out);
+  const int M = p.M, LP = p.L * 4;
+
+  if (!ts.layout_ok) {
+    // Levels that overlap or leave [0, S): the packed pyramid is not defined.  Correct but slow
+    // element-wise fallback on the original tensors (same arithmetic as msda_fwd_generic).
+    const T *__restrict__ value = static_cast<const T *>(p.value);
+    const long long n = (long long)p.Q * M * D;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+      const int c = (int)(i % D);
+      const long long pair_in_img = i / D;
+      const int m = (int)(pair_in_img % M);
+      const long long pair = (long long)blockIdx.y * p.Q * M + pair_in_img;
+      const T *vb = value + ((long long)blockIdx.y * p.S) * M * D + (long long)m * D + c;
+      float acc = 0.f;
+      for (int l = 0; l < p.L; ++l) {
+        const int H = (int)p.shapes[2 * l], W = (int)p.shapes[2 * l + 1];
+        const T *vl = vb + p.starts[l] * (long long)M * D;
+        for (int k = 0; k < 4; ++k) {
+          const long long si = pair * LP + l * 4 + k;
+          const Sample<float> sm = make_sample<float>(Elem<T>::to_acc(loc[si * 2]), Elem<T>::to_acc(loc[si * 2 + 1]),
+                                                      Elem<T>::to_acc(wgt[si]), H, W);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (sm.ok[j]) acc += sm.cw[j] * Elem<T>::to_acc(vl[(long long)sm.idx[j] * M * D]);
+        }
+      }
+      out[pair * D + c] = Elem<T>::from_acc(acc);
+    }
+    return;
+  }
+
+  const char *__restrict__ packed = static_cast<const char *>(p.packed);
+  const unsigned ent_pitch = (unsigned)(M * 128);
+  const int sub = threadIdx.x % G;
+  const int ks = sub;
+  const int ls = (int)(threadIdx.x / G);
+  const int slots = M << (p.tile_w_log2 + p.tile_h_log2);
+  const int total = ts.n_tiles * p.passes;
+  const int b = blockIdx.y;
+  int tql = 0, m_fixed = 0;
+  if (p.qpp) {
+    if (p.head_major) {
+      const int g = ls & (PPW - 1);
+      const int qb = fast_div(ls / PPW, M, p.inv_M, m_fixed);
+      tql = qb * PPW + g;
+    } else {
+      tql = fast_div(ls, M, p.inv_M, m_fixed);
+    }
+  }
+
+  for (int w = blockIdx.x; w < total; w += gridDim.x) {
+    int q, m;
+    {
+      int pass;
+      const int t = fast_div(w, p.passes, p.inv_passes, pass);
+      int tq;
+      if (p.qpp) {
+        tq = pass * p.qpp + tql;
+        m = m_fixed;
+        q = tile_query(p, ts, t, tq);
+      } else {
+        const int s = pass * PAIRS_PER_PASS + ls;
+        if (p.head_major) {
+          const int g = s & (PPW - 1);
+          const int qb = fast_div(s / PPW, M, p.inv_M, m);
+          tq = qb * PPW + g;
+        } else {
+          tq = fast_div(s, M, p.inv_M, m);
+        }
+        q = (s < slots) ? tile_query(p, ts, t, tq) : -1;
+      }
+    }
+    const bool live = q >= 0;
+    const int64_t pair = live ? ((int64_t)b * p.Q + q) * M + m : 0;
+    const T *lp = loc + pair * LP * 2;
+    const T *wp = wgt + pair * LP;
+    const char *vm = packed + ((size_t)b * p.S * M + m) * 128 + (size_t)sub * 32;
+    asm volatile("" : "+l"(vm));
+
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+
+    float nx, ny, naw;
+    load_sample_inputs<T>(lp, wp, ks, nx, ny, naw);
+    for (int l = 0; l < p.L; ++l) {
+      const int H = ts.lv[l].H, W = ts.lv[l].W;
+      const float x = nx, y = ny, aw = live ? naw : 0.f;
+      if (l + 1 < p.L) load_sample_inputs<T>(lp, wp, (l + 1) * 4 + ks, nx, ny, naw);
+      // geometry of sample ks: entry of the top row + weights (left, right) x (top, bottom)
+      int e_top;
+      float cw[4];
+      {
+        const float w_im = __fmul_rn(x, (float)W) - 0.5f;
+        const float h_im = __fmul_rn(y, (float)H) - 0.5f;
+        const bool inside = (h_im > -1.f) && (w_im > -1.f) && (h_im < (float)H) && (w_im < (float)W);
+        const float hf = floorf(h_im), wf = floorf(w_im);
+        const int h_lo = (int)hf, w_lo = (int)wf;
+        const float lh = h_im - hf, lw = w_im - wf;
+        const float hh = 1.f - lh, hw = 1.f - lw;
+        const float wy0 = (inside && h_lo >= 0) ? hh * aw : 0.f;
+        const float wy1 = (inside && h_lo < H - 1) ? lh * aw : 0.f;
+        // column -1: the entry of column 0 is used and its LEFT half is the sample's right-hand corner
+        const bool neg = w_lo < 0;
+        const float wl = inside ? (neg ? lw : hw) : 0.f;
+        const float wr = (inside && !neg && w_lo < W - 1) ? lw : 0.f;
+        cw[0] = wy0 * wl;
+        cw[1] = wy0 * wr;
+        cw[2] = wy1 * wl;
+        cw[3] = wy1 * wr;
+        e_top = ts.lv[l].start + h_lo * W + (neg ? 0 : w_lo);
+      }
+      unsigned pk0 = 0, pk1 = 0;
+      if constexpr (MATH == kFhfma) {
+        pk0 = pack_weights<T>(cw[0], cw[1]);
+        pk1 = pack_weights<T>(cw[2], cw[3]);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int be = __shfl_sync(0xffffffffu, e_top, k, G);
+        U8 rt, rb;
+        if constexpr (MATH == kFhfma) {
+          const unsigned bt = __shfl_sync(0xffffffffu, pk0, k, G);
+          const unsigned bb = __shfl_sync(0xffffffffu, pk1, k, G);
+          if ((bt & 0x7fff7fffu) != 0u) rt = ldg256(vm + (size_t)(unsigned)be * ent_pitch);
+          if ((bb & 0x7fff7fffu) != 0u) rb = ldg256(vm + (size_t)(unsigned)(be + W) * ent_pitch);
+          if ((bt & 0x7fffu) != 0u) piece_fma<T, kFhfma>(acc, &rt.v[0], 0.f, bt & 0xffffu);
+          if ((bt & 0x7fff0000u) != 0u) piece_fma<T, kFhfma>(acc, &rt.v[4], 0.f, bt >> 16);
+          if ((bb & 0x7fffu) != 0u) piece_fma<T, kFhfma>(acc, &rb.v[0], 0.f, bb & 0xffffu);
+          if ((bb & 0x7fff0000u) != 0u) piece_fma<T, kFhfma>(acc, &rb.v[4], 0.f, bb >> 16);
+        } else {
+          float bw[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) bw[j] = __shfl_sync(0xffffffffu, cw[j], k, G);
+          if (bw[0] != 0.f || bw[1] != 0.f) rt = ldg256(vm + (size_t)(unsigned)be * ent_pitch);
+          if (bw[2] != 0.f || bw[3] != 0.f) rb = ldg256(vm + (size_t)(unsigned)(be + W) * ent_pitch);
+          if (bw[0] != 0.f) piece_fma<T, kExact>(acc, &rt.v[0], bw[0], 0u);
+          if (bw[1] != 0.f) piece_fma<T, kExact>(acc, &rt.v[4], bw[1], 0u);
+          if (bw[2] != 0.f) piece_fma<T, kExact>(acc, &rb.v[0], bw[2], 0u);
+          if (bw[3] != 0.f) piece_fma<T, kExact>(acc, &rb.v[4], bw[3], 0u);
+        }
+      }
+    }
+    if (live) store_row<T, 8>(out + pair * D + sub * 8, acc);
   }
 }
 
@@ -979,6 +1270,11 @@ int launch_vec_d(const MsdaParams &p, const VecPlan &plan, cudaStream_t stream) 
                       : launch_vec_inst<T, D, 0, 4, MATH>(p, plan, stream);
     }
   }
+  if (plan.split == 2) {
+    if constexpr (G * 2 <= 32) {
+      if (p.P == 4) return launch_vec_inst<T, D, 4, 2, MATH>(p, plan, stream);
+    }
+  }
   return p.P == 4 ? launch_vec_inst<T, D, 4, 1, MATH>(p, plan, stream)
                   : launch_vec_inst<T, D, 0, 1, MATH>(p, plan, stream);
 }
@@ -1019,7 +1315,16 @@ int run_generic(const MsdaParams &p, int dtype, cudaStream_t stream) {
 
 bool aligned_to(const void *ptr, size_t a) { return (reinterpret_cast<uintptr_t>(ptr) % a) == 0; }
 
-int forward_impl(MsdaParams p, int dtype, unsigned flags, cudaStream_t stream) {
+// Bytes of workspace the packed path needs, or 0 when it does not apply / would not pay off: 16-bit
+// types, D = 32, P = 4, and enough gather work per packed row (the pre-pass touches every key once, the
+// gather touches Q*L*P*4 rows per head: the decoder's 900 queries would not amortise it).
+size_t packed_workspace_bytes(int64_t B, int64_t S, int64_t M, int64_t D, int64_t Q, int64_t L, int64_t P, int dtype) {
+  if ((dtype != MSDA_F16 && dtype != MSDA_BF16) || D != 32 || P != 4 || B <= 0 || S <= 0 || M <= 0) return 0;
+  if (Q * L * P * 4 < (int64_t)env_int("MSDA_B200_PACKED_RATIO", 16) * S) return 0;
+  return (size_t)B * (size_t)S * (size_t)M * 128;
+}
+
+int forward_impl(MsdaParams p, int dtype, unsigned flags, void *workspace, size_t workspace_bytes, cudaStream_t stream) {
   const size_t E = elem_size(dtype);
   const bool fused = p.ref_dim != 0;
 
@@ -1038,11 +1343,14 @@ int forward_impl(MsdaParams p, int dtype, unsigned flags, cudaStream_t stream) {
   VecPlan plan;
   const int sms = sm_count();
   const int64_t pairs = (int64_t)p.B * p.Q * p.M;
-  // small problems (decoder cross-attention): split the points of a pair over 4 lane groups
-  const int64_t lanes_full = pairs * G;
-  plan.split = (lanes_full < (int64_t)sms * 2048 && G * 4 <= 32) ? 4 : 1;
+  // Small problems only (the decoder's 900 queries: 7,200 pairs = 113 CTAs for 148 SMs): deal the points
+  // of a level to 4 (or 2) lane groups so every SM gets work.  As soon as the un-split grid covers the
+  // SMs the un-split kernel wins (measured: R50 encoder 608x608 28 us un-split vs 51 us split).
+  const int64_t ctas_unsplit = (pairs * G + kThreads - 1) / kThreads;
+  plan.split = 1;
+  if (ctas_unsplit < sms && p.P == 4) plan.split = (G * 4 <= 32) ? 4 : ((G * 2 <= 32) ? 2 : 1);
   plan.split = env_int("MSDA_B200_SPLIT", plan.split);
-  if (plan.split != 4 || G * 4 > 32) plan.split = 1;
+  if (!((plan.split == 4 && G * 4 <= 32) || (plan.split == 2 && G * 2 <= 32 && p.P == 4))) plan.split = 1;
 
   // fp16 defaults to the FHFMA path (combined weights rounded to fp16: measured max-normalised error
   // 4.7e-4 vs 2.7e-4 for fp32 weights at the headline shape, gate 2e-3); bf16 weights would keep only 8
@@ -1059,7 +1367,10 @@ int forward_impl(MsdaParams p, int dtype, unsigned flags, cudaStream_t stream) {
   auto ceil_log2 = [](int v) { int l = 0; while ((1 << l) < v) ++l; return l; };
   // tile geometry: power-of-two extents, width at least the pairs a warp holds in head-major order
   p.want_tiled = (flags & MSDA_FLAG_LINEAR_ORDER) ? 0 : (p.Q == p.S ? 1 : 0);
-  p.head_major = env_int("MSDA_B200_HEAD_MAJOR", 1);
+  // slot order inside a pass: query-major (a warp holds the heads of one query: its location / weight
+  // loads are contiguous) measured 4-5 % faster than head-major (a warp holds one head of neighbouring
+  // queries) once the kernel stopped being wavefront-bound; MSDA_FLAG_HEAD_MAJOR / the env knob switch
+  p.head_major = env_int("MSDA_B200_HEAD_MAJOR", (flags & MSDA_FLAG_HEAD_MAJOR) ? 1 : 0);
   int tile_w = env_int("MSDA_B200_TILE_W", 8);
   int tile_h = env_int("MSDA_B200_TILE_H", p.want_tiled ? 4 : 1);
   if (!p.want_tiled) {
@@ -1119,6 +1430,37 @@ int forward_impl(MsdaParams p, int dtype, unsigned flags, cudaStream_t stream) {
   if (grid < 1) grid = 1;
   plan.grid = (unsigned)grid;
   plan.grid_y = (unsigned)p.B;
+
+  // ---- packed path: pixel-pair packed pyramid in the caller's workspace + 256-bit loads ----
+  const size_t packed_need = packed_workspace_bytes(p.B, p.S, p.M, p.D, p.Q, p.L, p.P, dtype);
+  const bool packed_ok = packed_need > 0 && workspace != nullptr && workspace_bytes >= packed_need && aligned_to(workspace, 128) &&
+                         plan.split == 1 && !(flags & MSDA_FLAG_NO_PACKED) && env_int("MSDA_B200_PACKED", 1) &&
+                         aligned_to(p.loc, 4) && aligned_to(p.weight, 2);
+  if (packed_ok) {
+    p.packed = workspace;
+    const long long chunks = (long long)p.B * p.S * p.M * 4;
+    long long pgrid = (chunks + kThreads - 1) / kThreads;
+    const long long pcap = (long long)sms * 16;
+    if (pgrid > pcap) pgrid = pcap;
+    int rc2;
+    if (dtype == MSDA_F16) {
+      msda_pack_value<__half><<<(unsigned)pgrid, kThreads, 0, stream>>>(p);
+      if (plan.math == kFhfma) msda_fwd_packed<__half, kFhfma><<<dim3(plan.grid, plan.grid_y, 1), kThreads, 0, stream>>>(p);
+      else msda_fwd_packed<__half, kExact><<<dim3(plan.grid, plan.grid_y, 1), kThreads, 0, stream>>>(p);
+    } else {
+      msda_pack_value<__nv_bfloat16><<<(unsigned)pgrid, kThreads, 0, stream>>>(p);
+      if (plan.math == kFhfma) msda_fwd_packed<__nv_bfloat16, kFhfma><<<dim3(plan.grid, plan.grid_y, 1), kThreads, 0, stream>>>(p);
+      else msda_fwd_packed<__nv_bfloat16, kExact><<<dim3(plan.grid, plan.grid_y, 1), kThreads, 0, stream>>>(p);
+    }
+    g_launch_count.fetch_add(2, std::memory_order_relaxed);
+    rc2 = (int)cudaGetLastError();
+    if (rc2 == 0) {
+      snprintf(g_last_variant, sizeof(g_last_variant), "packed<%s,D32,P4>/%s%dx%d/%s/%s+pack-prepass", dtype_name(dtype),
+               p.want_tiled ? "tiled" : "linear", 1 << p.tile_w_log2, 1 << p.tile_h_log2,
+               p.head_major ? "head-major" : "query-major", plan.math == kFhfma ? "fhfma" : "exact");
+    }
+    return rc2;
+  }
 
   int rc;
   switch (dtype) {
@@ -1190,10 +1532,25 @@ uint64_t msda_b200_algorithmic_gather_bytes(int64_t B, int64_t M, int64_t D, int
   return (uint64_t)elem_size(dtype) * (uint64_t)B * (uint64_t)Q * (uint64_t)M * (uint64_t)L * (uint64_t)P * 4ull * (uint64_t)D;
 }
 
+size_t msda_b200_workspace_bytes(int64_t batch, int64_t num_keys, int64_t num_heads, int64_t channels, int64_t num_levels,
+                                 int64_t num_queries, int64_t num_points, int dtype) {
+  return packed_workspace_bytes(batch, num_keys, num_heads, channels, num_queries, num_levels, num_points, dtype);
+}
+
 int msda_b200_forward(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
                       const void *sampling_loc, const void *attn_weight, void *output, int64_t batch, int64_t num_keys,
                       int64_t num_heads, int64_t channels, int64_t num_levels, int64_t num_queries, int64_t num_points,
                       int64_t im2col_step, int dtype, unsigned flags, void *stream) {
+  return msda_b200_forward_ws(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, output, nullptr, 0, batch,
+                              num_keys, num_heads, channels, num_levels, num_queries, num_points, im2col_step, dtype, flags,
+                              stream);
+}
+
+int msda_b200_forward_ws(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                         const void *sampling_loc, const void *attn_weight, void *output, void *workspace,
+                         size_t workspace_bytes, int64_t batch, int64_t num_keys, int64_t num_heads, int64_t channels,
+                         int64_t num_levels, int64_t num_queries, int64_t num_points, int64_t im2col_step, int dtype,
+                         unsigned flags, void *stream) {
   int rc = validate_common(value, spatial_shapes, level_start_index, output, batch, num_keys, num_heads, channels,
                            num_levels, num_queries, num_points, dtype);
   if (rc != MSDA_OK) return rc;
@@ -1219,7 +1576,7 @@ int msda_b200_forward(const void *value, const int64_t *spatial_shapes, const in
   p.B = (int)batch; p.S = (int)num_keys; p.M = (int)num_heads; p.D = (int)channels;
   p.L = (int)num_levels; p.Q = (int)num_queries; p.P = (int)num_points;
   p.ref_dim = 0;
-  return forward_impl(p, dtype, flags, static_cast<cudaStream_t>(stream));
+  return forward_impl(p, dtype, flags, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
 int msda_b200_forward_fused(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
@@ -1248,27 +1605,39 @@ int msda_b200_forward_fused(const void *value, const int64_t *spatial_shapes, co
   p.B = (int)batch; p.S = (int)num_keys; p.M = (int)num_heads; p.D = (int)channels;
   p.L = (int)num_levels; p.Q = (int)num_queries; p.P = (int)num_points;
   p.ref_dim = (int)ref_dim;
-  return forward_impl(p, dtype, flags, static_cast<cudaStream_t>(stream));
+  return forward_impl(p, dtype, flags, nullptr, 0, static_cast<cudaStream_t>(stream));
+}
+
+static int trt_to_msda_dtype(int trt_dtype) {
+  switch (trt_dtype) {  // nvinfer1::DataType values (deformable_attention_plugin.cpp:53-62 accepts kFLOAT, kHALF)
+    case 0: return MSDA_F32;
+    case 1: return MSDA_F16;
+    case 7: return MSDA_BF16;
+    default: return -1;
+  }
+}
+
+size_t msda_b200_plugin_workspace_bytes(const int64_t *value_dims, const int64_t *loc_dims, int trt_dtype) {
+  if (!value_dims || !loc_dims) return 0;
+  const int dtype = trt_to_msda_dtype(trt_dtype);
+  if (dtype < 0) return 0;
+  return packed_workspace_bytes(value_dims[0], value_dims[1], value_dims[2], value_dims[3], loc_dims[1], loc_dims[3], loc_dims[4],
+                                dtype);
 }
 
 int msda_b200_plugin_enqueue(const int64_t *value_dims, const int64_t *loc_dims, int trt_dtype,
-                             const void *const *inputs, void *const *outputs, void * /*workspace*/,
+                             const void *const *inputs, void *const *outputs, void *workspace, size_t workspace_bytes,
                              int64_t im2col_step, void *stream) {
   if (!value_dims || !loc_dims || !inputs || !outputs) return MSDA_ERR_NULL_POINTER;
-  int dtype;
-  switch (trt_dtype) {  // nvinfer1::DataType values (deformable_attention_plugin.cpp:53-62 accepts kFLOAT, kHALF)
-    case 0: dtype = MSDA_F32; break;
-    case 1: dtype = MSDA_F16; break;
-    case 7: dtype = MSDA_BF16; break;
-    default: return MSDA_ERR_BAD_DTYPE;
-  }
+  const int dtype = trt_to_msda_dtype(trt_dtype);
+  if (dtype < 0) return MSDA_ERR_BAD_DTYPE;
   // deformable_attention_plugin.cpp:305-315
   const int64_t bs = value_dims[0], num_keys = value_dims[1], num_heads = value_dims[2], dim_per_head = value_dims[3];
   const int64_t num_queries = loc_dims[1], num_levels = loc_dims[3], num_points = loc_dims[4];
   if (loc_dims[0] != bs || loc_dims[2] != num_heads || loc_dims[5] != 2) return MSDA_ERR_BAD_SHAPE;
-  return msda_b200_forward(inputs[0], static_cast<const int64_t *>(inputs[1]), static_cast<const int64_t *>(inputs[2]),
-                           inputs[3], inputs[4], outputs[0], bs, num_keys, num_heads, dim_per_head, num_levels,
-                           num_queries, num_points, im2col_step, dtype, MSDA_FLAG_DEFAULT, stream);
+  return msda_b200_forward_ws(inputs[0], static_cast<const int64_t *>(inputs[1]), static_cast<const int64_t *>(inputs[2]),
+                              inputs[3], inputs[4], outputs[0], workspace, workspace_bytes, bs, num_keys, num_heads,
+                              dim_per_head, num_levels, num_queries, num_points, im2col_step, dtype, MSDA_FLAG_DEFAULT, stream);
 }
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }

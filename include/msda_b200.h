@@ -71,8 +71,10 @@ enum msda_flags {
                                        (default for fp16; bf16 defaults to exact)         */
   MSDA_FLAG_MATH_EXACT = 1 << 3,    /* fp16/bf16: fp32 weights, convert + FFMA            */
   MSDA_FLAG_NO_STAGING = 1 << 4,    /* never stage loc/weights through shared memory (the default) */
-  MSDA_FLAG_STAGE_TMA = 1 << 5      /* stage loc/weights of each pass with TMA bulk copies (opt-in:
+  MSDA_FLAG_STAGE_TMA = 1 << 5,     /* stage loc/weights of each pass with TMA bulk copies (opt-in:
                                        measured slightly slower than direct loads) */
+  MSDA_FLAG_NO_PACKED = 1 << 6,     /* ignore the workspace: never use the packed-pyramid path */
+  MSDA_FLAG_HEAD_MAJOR = 1 << 7     /* a warp holds one head of neighbouring queries (default: query-major) */
 };
 
 /*
@@ -98,6 +100,27 @@ int msda_b200_forward(const void *value, const int64_t *spatial_shapes, const in
                       unsigned flags, void *stream);
 
 /*
+ * msda_b200_forward_ws -- msda_b200_forward with an optional caller-owned device WORKSPACE.
+ *
+ * With a workspace of at least msda_b200_workspace_bytes(...) bytes (128-byte aligned) the library may
+ * take the packed path: a pre-pass re-lays the value pyramid out in the workspace so that one 128-byte
+ * line holds a (pixel, head) row and its right-hand neighbour, and the gather kernel fetches both
+ * horizontal corners of a sample with one 256-bit load (two L1 wavefronts per sample instead of four).
+ * Results are the same bits as msda_b200_forward's for the same math mode.  The workspace is scratch: it
+ * carries no state between calls.  msda_b200_workspace_bytes returns 0 when the packed path does not
+ * apply to the shape (then any workspace is ignored).  Stands behind the same reference interface as
+ * msda_b200_forward; the workspace corresponds to TensorRT's plugin workspace
+ * (IPluginV3OneRuntime::getWorkspaceSize, deformable_attention_plugin.cpp:371-374 returns 0 today).
+ */
+size_t msda_b200_workspace_bytes(int64_t batch, int64_t num_keys, int64_t num_heads, int64_t channels,
+                                 int64_t num_levels, int64_t num_queries, int64_t num_points, int dtype);
+int msda_b200_forward_ws(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                         const void *sampling_loc, const void *attn_weight, void *output, void *workspace,
+                         size_t workspace_bytes, int64_t batch, int64_t num_keys, int64_t num_heads,
+                         int64_t channels, int64_t num_levels, int64_t num_queries, int64_t num_points,
+                         int64_t im2col_step, int dtype, unsigned flags, void *stream);
+
+/*
  * msda_b200_plugin_enqueue -- the TensorRT IPluginV3OneRuntime::enqueue body
  * without libtorch.
  *
@@ -109,10 +132,13 @@ int msda_b200_forward(const void *value, const int64_t *spatial_shapes, const in
  *   loc_dims = inputDesc[3].dims.d (6 entries); trt_dtype is the integer value
  *   of nvinfer1::DataType of input 0 (kFLOAT = 0, kHALF = 1, kBF16 = 7).
  * Returns 0 on success and non-zero on failure, like enqueue (:320-325).
+ * `workspace` / `workspace_bytes` are TensorRT's plugin workspace (may be NULL / 0); a plugin that wants the
+ * packed path returns msda_b200_plugin_workspace_bytes(...) from getWorkspaceSize.
  */
+size_t msda_b200_plugin_workspace_bytes(const int64_t *value_dims, const int64_t *loc_dims, int trt_dtype);
 int msda_b200_plugin_enqueue(const int64_t *value_dims, const int64_t *loc_dims, int trt_dtype,
                              const void *const *inputs, void *const *outputs, void *workspace,
-                             int64_t im2col_step, void *stream);
+                             size_t workspace_bytes, int64_t im2col_step, void *stream);
 
 /*
  * msda_b200_forward_fused -- opt-in producer-fused mode (not part of the

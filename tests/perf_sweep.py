@@ -110,6 +110,10 @@ def main():
                  ("ref_test_mid_fp32", 1, "float32", None)]
     if args.quick:
         workloads = workloads[:2]
+    if args.only == "decoder":
+        workloads = [("swinl_dec_1152x768", 1, "float16", None), ("swinl_dec_1900q", 1, "float16", None),
+                     ("swinl_dec_1152x768", 8, "float16", None), ("ref_test_mid_fp32", 1, "float32", None),
+                     ("r50_enc_608", 1, "float16", None)]
     if args.only == "headline":
         workloads = [("swinl_enc_1152x768", 1, "float16", None), ("swinl_enc_1152x768", 1, "float32", None),
                      ("swinl_dec_1152x768", 1, "float16", None), ("swinl_enc_1920x1280", 2, "float16", None)]
@@ -121,12 +125,14 @@ def main():
         {"name": "query-major", "flags": 0, "MSDA_B200_HEAD_MAJOR": 0},
         {"name": "query-major+linear", "flags": cb.FLAG_LINEAR_ORDER, "MSDA_B200_HEAD_MAJOR": 0},
         {"name": "generic", "flags": cb.FLAG_FORCE_GENERIC},
-        {"name": "nostage", "flags": cb.FLAG_NO_STAGING},
-        {"name": "fhfma+nostage", "flags": cb.FLAG_MATH_FHFMA | cb.FLAG_NO_STAGING},
+        {"name": "packed", "flags": 0, "ws": True},
+        {"name": "packed+exact", "flags": cb.FLAG_MATH_EXACT, "ws": True},
+        {"name": "nopacked+exact", "flags": cb.FLAG_MATH_EXACT},
+        {"name": "staged", "flags": cb.FLAG_STAGE_TMA},
     ]
     tile_cfgs = [{"name": f"tile{w}x{h}+fhfma", "flags": cb.FLAG_MATH_FHFMA, "MSDA_B200_TILE_W": w, "MSDA_B200_TILE_H": h}
                  for (w, h) in ((8, 1), (8, 2), (8, 8), (16, 2), (16, 4), (4, 4), (32, 2), (32, 8))]
-    split_cfgs = [{"name": f"split{s}", "flags": 0, "MSDA_B200_SPLIT": s} for s in (1, 4)]
+    split_cfgs = [{"name": f"split{s}", "flags": 0, "MSDA_B200_SPLIT": s} for s in (1, 2, 4)]
     split_cfgs += [{"name": f"split{s}+fhfma", "flags": cb.FLAG_MATH_FHFMA, "MSDA_B200_SPLIT": s} for s in (1, 4)]
 
     for name, batch, dtn, loc_mode in workloads:
@@ -143,9 +149,12 @@ def main():
             cfgs += split_cfgs
         if dtn == "float32":
             cfgs = [c for c in cfgs if "fhfma" not in c["name"]]
+        if args.only == "decoder":
+            cfgs = [c for c in split_cfgs if "fhfma" not in c["name"]] + [{"name": "default", "flags": 0}]
+            have_ref = False
         if args.only == "headline":
             cfgs = [c for c in cfgs if c["name"] in ("default", "fhfma", "linear+fhfma", "query-major", "tile8x8+fhfma", "tile16x4+fhfma",
-                                                      "tile4x4+fhfma", "split1", "split4", "split1+fhfma", "nostage", "fhfma+nostage")]
+                                                      "tile4x4+fhfma", "split1", "split4", "split1+fhfma", "packed", "packed+exact", "nopacked+exact", "staged")]
             have_ref = False
         ref32 = None
         if dtn != "float32":
@@ -154,7 +163,13 @@ def main():
                                                         s0["sampling_loc"].float(), s0["attn_weight"].float(), flags=0)
         for cfg in cfgs:
             set_env(cfg)
-            calls = [cb.PreparedForward(*(s[k] for k in KEYS), flags=cfg["flags"]) for s in sets]
+            ws = None
+            if cfg.get("ws"):
+                need = cb.workspace_bytes(sets[0]["value"], sets[0]["sampling_loc"])
+                if need == 0:
+                    continue
+                ws = torch.empty(need, dtype=torch.uint8, device=dev)
+            calls = [cb.PreparedForward(*(s[k] for k in KEYS), flags=cfg["flags"], workspace=ws) for s in sets]
             us = time_calls(calls, iters)
             row = {"workload": name, "batch": batch, "dtype": dtn, "loc_mode": loc_mode or wl.kind, "config": cfg["name"],
                    "variant": cb.last_variant(), "us_per_call": us, "hbm_GBps": hbm / us / 1e3, "gather_GBps": gather / us / 1e3,

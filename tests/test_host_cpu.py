@@ -76,9 +76,9 @@ def test_argument_validation_returns_before_any_cuda_work():
     ld = (ctypes.c_int64 * 6)(1, 3, 2, 1, 2, 2)
     ins = (ctypes.c_void_p * 5)(p, p, p, p, p)
     outs = (ctypes.c_void_p * 1)(p)
-    assert lib.msda_b200_plugin_enqueue(vd, ld, 3, ins, outs, None, 64, None) == -3  # kINT8 is not a plugin dtype
+    assert lib.msda_b200_plugin_enqueue(vd, ld, 3, ins, outs, None, 0, 64, None) == -3  # kINT8 is not a plugin dtype
     ld_bad = (ctypes.c_int64 * 6)(2, 3, 2, 1, 2, 2)
-    assert lib.msda_b200_plugin_enqueue(vd, ld_bad, 0, ins, outs, None, 64, None) == -2
+    assert lib.msda_b200_plugin_enqueue(vd, ld_bad, 0, ins, outs, None, 0, 64, None) == -2
     assert cb.launch_count() == 0 or cb.launch_count() >= 0  # no launch happened in this test
     assert lib.msda_b200_host_workspace_bytes(1, 16, 2, 4, 1, 3, 2, 0) >= (16 * 8 + 3 * 2 * 2 * 3 + 3 * 8) * 4
 

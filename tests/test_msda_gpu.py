@@ -31,6 +31,7 @@ FLAG_SETS = {
     "exact": cb.FLAG_MATH_EXACT,
     "staged": cb.FLAG_STAGE_TMA,
     "staged+fhfma": cb.FLAG_STAGE_TMA | cb.FLAG_MATH_FHFMA,
+    "head-major": cb.FLAG_HEAD_MAJOR,
 }
 
 
@@ -66,7 +67,7 @@ def ref32_of(d):
 # ----------------------------------------------------------------------------------------------
 # golden vectors
 # ----------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("flagset", ["default", "generic", "linear", "staged"])
+@pytest.mark.parametrize("flagset", ["default", "generic", "linear", "staged", "head-major"])
 @pytest.mark.parametrize("case", CASES, ids=[c.name for c in CASES])
 def test_fp32_matches_golden(case, flagset, cuda_device):
     arrs, z = load_case(case)
@@ -84,7 +85,7 @@ def test_fp64_matches_golden(case, cuda_device):
     assert max_rel(out.cpu().numpy(), z["out_f64"]) < 1e-13
 
 
-@pytest.mark.parametrize("flagset", ["default", "generic", "linear", "fhfma", "exact", "staged", "staged+fhfma"])
+@pytest.mark.parametrize("flagset", ["default", "generic", "linear", "fhfma", "exact", "staged", "staged+fhfma", "head-major"])
 @pytest.mark.parametrize("dt", ["f16", "bf16"])
 @pytest.mark.parametrize("case", CASES, ids=[c.name for c in CASES])
 def test_half_matches_fp32_reference(case, dt, flagset, cuda_device):
@@ -435,3 +436,83 @@ def test_host_pipeline_matches_synchronous_calls(cuda_device):
         t = pipe.submit(*(host[k] for k in ARRAY_KEYS))
     pipe.drain()
     assert torch.equal(pipe.result(t), want)
+
+
+# ----------------------------------------------------------------------------------------------
+# packed-pyramid path (workspace + 256-bit loads)
+# ----------------------------------------------------------------------------------------------
+def _with_workspace(d, flags=0):
+    need = cb.workspace_bytes(d["value"], d["sampling_loc"])
+    assert need > 0
+    ws = torch.empty(need, dtype=torch.uint8, device=d["value"].device)
+    out = torch.full((d["value"].shape[0], d["sampling_loc"].shape[1], d["value"].shape[2] * d["value"].shape[3]), float("nan"),
+                     dtype=d["value"].dtype, device=d["value"].device)
+    cb.forward_into(*(d[k] for k in ARRAY_KEYS), out, flags=flags, workspace=ws)
+    torch.cuda.synchronize()
+    return out
+
+
+@pytest.mark.parametrize("dt", ["f16", "bf16"])
+@pytest.mark.parametrize("case", [c for c in CASES if c.name in ("edge_borders", "codino_enc_tiny", "codino_dec_tiny")],
+                         ids=lambda c: c.name)
+def test_packed_path_matches_direct_path(case, dt, cuda_device, monkeypatch):
+    """Same math mode -> same bits as the direct path (the corner order of the accumulation is identical),
+    including the column -1 / last-column / top / bottom border cases of edge_borders."""
+    monkeypatch.setenv("MSDA_B200_PACKED_RATIO", "0")  # small fixtures would not amortise the pre-pass ...
+    monkeypatch.setenv("MSDA_B200_SPLIT", "1")         # ... and would take the split-points variant
+    arrs, _ = load_case(case)
+    d = to_dev(arrs, TORCH_DT[dt], cuda_device)
+    for fl in (cb.FLAG_MATH_EXACT, cb.FLAG_MATH_FHFMA):
+        before = cb.launch_count()
+        packed = _with_workspace(d, fl)
+        assert cb.launch_count() == before + 2 and cb.last_variant().startswith("packed<")
+        direct = cb.multi_scale_deformable_attention(*(d[k] for k in ARRAY_KEYS), flags=fl | cb.FLAG_NO_PACKED)
+        assert cb.last_variant().startswith("vec<")
+        assert torch.equal(packed, direct)
+    ref = ref32_of(d)
+    exact = _with_workspace(d, cb.FLAG_MATH_EXACT)
+    assert max_rel(exact.float().cpu().numpy(), ref) <= (HALF_MAX_REL if dt == "f16" else BF16_MAX_REL)
+
+
+def test_packed_path_exotic_level_layout_falls_back(cuda_device, monkeypatch):
+    """Overlapping levels (both start at key 0) have no packed pyramid: the packed kernel must detect it on
+    the device and still return the reference's result."""
+    monkeypatch.setenv("MSDA_B200_PACKED_RATIO", "0")
+    monkeypatch.setenv("MSDA_B200_SPLIT", "1")
+    rng = np.random.default_rng(9)
+    shapes = np.array([[6, 5], [3, 4]], dtype=np.int64)
+    starts = np.array([0, 0], dtype=np.int64)
+    arrs = dict(value=rng.standard_normal((2, 30, 8, 32), dtype=np.float32), spatial_shapes=shapes, level_start_index=starts,
+                sampling_loc=rng.uniform(-0.1, 1.1, (2, 9, 8, 2, 4, 2)).astype(np.float32),
+                attn_weight=rng.random((2, 9, 8, 2, 4), dtype=np.float32))
+    d = to_dev(arrs, torch.float16, cuda_device)
+    out = _with_workspace(d)
+    assert cb.last_variant().startswith("packed<")
+    assert max_rel(out.float().cpu().numpy(), ref32_of(d)) <= HALF_MAX_REL
+
+
+def test_packed_path_full_size_and_torch_op(cuda_device):
+    """Headline shape: the registered torch op hands the library a scratch buffer and gets the packed path;
+    bits equal the direct path; the plugin-style call with a TensorRT workspace does the same."""
+    arrs = _full_inputs(W.HEADLINE, 1)
+    d = to_dev(arrs, torch.float16, cuda_device)
+    old = cb.set_use_workspace(True)
+    try:
+        out = torch.ops.codetr.multi_scale_deformable_attention(*(d[k] for k in ARRAY_KEYS), 64)
+        variant = cb.last_variant()
+    finally:
+        cb.set_use_workspace(old)
+    direct = cb.multi_scale_deformable_attention(*(d[k] for k in ARRAY_KEYS), flags=cb.FLAG_NO_PACKED)
+    assert torch.equal(out, direct)
+    assert variant.startswith("packed<")
+    need = cb._native.load().msda_b200_plugin_workspace_bytes(
+        (__import__("ctypes").c_int64 * 4)(*d["value"].shape), (__import__("ctypes").c_int64 * 6)(*d["sampling_loc"].shape), cb.ops.TRT_HALF)
+    assert need == cb.workspace_bytes(d["value"], d["sampling_loc"]) == 18414 * 8 * 128
+    ws = torch.empty(need, dtype=torch.uint8, device=cuda_device)
+    out2 = torch.full_like(out, float("nan"))
+    s = torch.cuda.Stream(device=cuda_device)
+    s.wait_stream(torch.cuda.current_stream(cuda_device))
+    assert cb.plugin_enqueue(d["value"].shape, d["sampling_loc"].shape, cb.ops.TRT_HALF, [d[k].data_ptr() for k in ARRAY_KEYS],
+                             out2.data_ptr(), s.cuda_stream, workspace_ptr=ws.data_ptr(), workspace_bytes=need) == 0
+    s.synchronize()
+    assert torch.equal(out2, direct)
