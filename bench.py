@@ -55,6 +55,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cuda-graph", action="store_true", help="replay the K steps from one captured CUDA graph")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the bounded CPU sample")
+    ap.add_argument("--no-batch-sweep", action="store_true", help="skip the extra per-GPU batch 2/4/8 rows (N=1 only)")
     return ap.parse_args()
 
 
@@ -372,6 +373,38 @@ def run_b200(args):
                "api": "codetr_b200.HostPipeline(depth=3) -> msda_b200_forward_host (pinned host buffers, "
                       "H2D of all inputs + kernel + D2H of the result every step)"}
 
+    # ---- extra rows (N=1 only): the same workload at larger per-GPU batches, one launch per batch ----
+    batch_sweep = None
+    if world == 1 and not args.no_batch_sweep:
+        batch_sweep = {}
+        for bsz in (2, 4, 8):
+            if bsz == batch:
+                continue
+            inp_b = W.make_inputs(wl, batch=bsz, seed=wl.seed + 77, loc_mode=args.loc_mode)
+            sets_b = []
+            n_b = max(2, -(-int(1.5 * L2_BYTES) // W.algorithmic_hbm_bytes(wl, bsz, esize)))
+            for i in range(n_b):
+                d = {}
+                for k in keys:
+                    t = torch.from_numpy(getattr(inp_b, k))
+                    d[k] = t.to(dev) if t.dtype == torch.int64 else t.to(device=dev, dtype=dt)
+                sets_b.append(cb.PreparedForward(*(d[k] for k in keys), flags=args.flags))
+            for i in range(5):
+                sets_b[i % n_b](sptr)
+            torch.cuda.synchronize()
+            iters = max(20, min(args.steps, 400) // bsz)
+            s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s_ev.record(stream)
+            for i in range(iters):
+                sets_b[i % n_b](sptr)
+            e_ev.record(stream)
+            torch.cuda.synchronize()
+            us = 1e3 * s_ev.elapsed_time(e_ev) / iters
+            batch_sweep[f"b{bsz}"] = {"us_per_call": us, "images_per_s": bsz / (us * 1e-6),
+                                      "gather_GBps": W.algorithmic_gather_bytes(wl, bsz, esize) / us / 1e3}
+            del sets_b
+            torch.cuda.empty_cache()
+
     if use_dist:
         dist.destroy_process_group()
     if rank != 0:
@@ -413,7 +446,7 @@ def run_b200(args):
             "l2_policy": f"rotating {n_sets} distinct input sets, {n_sets * hbm_bytes / 1e6:.0f} MB > 126 MB L2",
             "launch": "cuda_graph" if graph is not None else "C ABI via ctypes, back to back on one stream",
         },
-        "roofline": roofline, "roofline_l2_gather": roofline_l2, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+        "roofline": roofline, "roofline_l2_gather": roofline_l2, "batch_sweep": batch_sweep, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
         "clocks": sampler.summary(),
     }
 
