@@ -186,6 +186,41 @@ __device__ __forceinline__ Sample<A> make_sample(A x, A y, A aw, int H, int W) {
 }
 
 // ---------------------------------------------------------------------------
+// Fused-producer mode (msda_b200_forward_fused): the softmax over L*P and the sampling-location
+// arithmetic of the calling module (codetr/multi_scale_deformable_attention.py:180-200) happen in the
+// kernel.  The module runs those steps as separate PyTorch ops in the tensor dtype, so for fp16/bf16 every
+// intermediate (off / normaliser, ref + ..., off / P, ... * wh, softmax output) is rounded to 16 bits; the
+// helpers below round at the same places, so the fused result tracks the unfused pipeline instead of
+// being "more exact" than it.  For float / double the roundings are identities.
+// ---------------------------------------------------------------------------
+template <typename T, typename A>
+__device__ __forceinline__ A round_like(A v) {
+  return (A)Elem<T>::to_acc(Elem<T>::from_acc((typename Elem<T>::acc_t)v));
+}
+
+// exp of the softmax: full-precision expf for fp32 tensors, the fast intrinsic when the result is rounded to 16 bits
+template <typename T>
+__device__ __forceinline__ float fused_exp(float v) {
+  if constexpr (sizeof(T) == 4) return expf(v);
+  else return __expf(v);
+}
+
+template <typename T, typename A>
+__device__ __forceinline__ void fused_location(const T *rf, int ref_dim, A ox, A oy, int H, int W, int P, A &x, A &y) {
+  if (ref_dim == 2) {
+    // reference_points + sampling_offsets / (W, H)        (:186-191)
+    x = round_like<T, A>((A)Elem<T>::to_acc(rf[0]) + round_like<T, A>(ox / (A)W));
+    y = round_like<T, A>((A)Elem<T>::to_acc(rf[1]) + round_like<T, A>(oy / (A)H));
+  } else {
+    // reference_points[..., :2] + sampling_offsets / P * reference_points[..., 2:] * 0.5   (:192-196)
+    const A tx = round_like<T, A>(round_like<T, A>(ox / (A)P) * (A)Elem<T>::to_acc(rf[2])) * (A)0.5;
+    const A ty = round_like<T, A>(round_like<T, A>(oy / (A)P) * (A)Elem<T>::to_acc(rf[3])) * (A)0.5;
+    x = round_like<T, A>((A)Elem<T>::to_acc(rf[0]) + tx);
+    y = round_like<T, A>((A)Elem<T>::to_acc(rf[1]) + ty);
+  }
+}
+
+// ---------------------------------------------------------------------------
 // Generic kernel: any D, any L, any P, any dtype (incl. double).  One thread per
 // output element; used for shapes the vector kernel does not cover and as the
 // in-library cross-check of the fast paths.  Fused mode is supported here too.
@@ -233,14 +268,8 @@ __global__ void __launch_bounds__(kThreads) msda_fwd_generic(const MsdaParams p)
           const T *of = static_cast<const T *>(p.offsets) + si * 2;
           const T *rf = static_cast<const T *>(p.ref) + (bq * p.L + l) * p.ref_dim;
           const A ox = Elem<T>::to_acc(of[0]), oy = Elem<T>::to_acc(of[1]);
-          if (p.ref_dim == 2) {
-            x = Elem<T>::to_acc(rf[0]) + ox / (A)W;
-            y = Elem<T>::to_acc(rf[1]) + oy / (A)H;
-          } else {
-            x = Elem<T>::to_acc(rf[0]) + ox / (A)p.P * Elem<T>::to_acc(rf[2]) * (A)0.5;
-            y = Elem<T>::to_acc(rf[1]) + oy / (A)p.P * Elem<T>::to_acc(rf[3]) * (A)0.5;
-          }
-          aw = exp(Elem<T>::to_acc(static_cast<const T *>(p.logits)[si]) - mx) / denom;
+          fused_location<T, A>(rf, p.ref_dim, ox, oy, H, W, p.P, x, y);
+          aw = round_like<T, A>(exp((A)Elem<T>::to_acc(static_cast<const T *>(p.logits)[si]) - mx) / denom);
         }
         const Sample<A> s = make_sample<A>(x, y, aw, H, W);
 #pragma unroll
@@ -651,7 +680,7 @@ __device__ __forceinline__ void pass_query_range(const MsdaParams &p, const Tile
 //         (small-Q / decoder shapes, to expose more parallelism)
 //   MATH  kExact: fp32 weights ; kFhfma: 16-bit weights + FHFMA
 // ---------------------------------------------------------------------------
-template <typename T, int D, int P_T, int SPLIT, int MATH, bool STAGE>
+template <typename T, int D, int P_T, int SPLIT, int MATH, bool STAGE, bool FUSED = false>
 __global__ void __launch_bounds__(kThreads, (SPLIT > 1 && P_T == 4) ? MSDA_MINB_SPLIT : MSDA_MINB) msda_fwd_vec(const MsdaParams p) {
   constexpr int E = (int)sizeof(T);
   constexpr int VEC = 16 / E;            // channels per lane
@@ -676,8 +705,9 @@ __global__ void __launch_bounds__(kThreads, (SPLIT > 1 && P_T == 4) ? MSDA_MINB_
   __syncthreads();
 
   const char *__restrict__ value = static_cast<const char *>(p.value);
-  const T *__restrict__ loc = static_cast<const T *>(p.loc);
-  const T *__restrict__ wgt = static_cast<const T *>(p.weight);
+  // fused mode: "loc" are the raw sampling offsets and "wgt" the pre-softmax logits (same layouts)
+  const T *__restrict__ loc = static_cast<const T *>(FUSED ? p.offsets : p.loc);
+  const T *__restrict__ wgt = static_cast<const T *>(FUSED ? p.logits : p.weight);
   T *__restrict__ out = static_cast<T *>(p.out);
 
   const int P = P_T ? P_T : p.P;
@@ -792,9 +822,31 @@ __global__ void __launch_bounds__(kThreads, (SPLIT > 1 && P_T == 4) ? MSDA_MINB_
         float nx, ny, naw;
         if constexpr (STAGE) load_sample_inputs_smem<T>(slp, swp, ks, nx, ny, naw);
         else load_sample_inputs<T>(lp, wp, ks, nx, ny, naw);
+        // fused mode: softmax statistics of the pair's L*4 logits.  Lane ks holds the logits of point ks
+        // of every level; maximum and sum are completed across the four point-lanes with two butterflies.
+        float sm_max = 0.f, sm_inv = 1.f;
+        const T *rfp = nullptr;
+        if constexpr (FUSED) {
+          float mx = -INFINITY;
+          for (int l = 0; l < p.L; ++l) mx = fmaxf(mx, Elem<T>::to_acc(wp[l * 4 + ks]));
+          mx = fmaxf(mx, __shfl_xor_sync(group_mask, mx, 1));
+          mx = fmaxf(mx, __shfl_xor_sync(group_mask, mx, 2));
+          float sum = 0.f;
+          for (int l = 0; l < p.L; ++l) sum += fused_exp<T>(Elem<T>::to_acc(wp[l * 4 + ks]) - mx);
+          sum += __shfl_xor_sync(group_mask, sum, 1);
+          sum += __shfl_xor_sync(group_mask, sum, 2);
+          sm_max = mx;
+          sm_inv = 1.f / sum;
+          rfp = static_cast<const T *>(p.ref) + ((int64_t)b * p.Q + (live ? q : 0)) * p.L * p.ref_dim;
+        }
         for (int l = 0; l < p.L; ++l) {
           const int H = ts.lv[l].H, W = ts.lv[l].W;
-          const float x = nx, y = ny, aw = live ? naw : 0.f;
+          float x = nx, y = ny, aw = live ? naw : 0.f;
+          if constexpr (FUSED) {
+            // nx, ny are the raw offsets, naw the logit
+            fused_location<T, float>(rfp + l * p.ref_dim, p.ref_dim, nx, ny, H, W, 4, x, y);
+            aw = live ? round_like<T, float>(fused_exp<T>(naw - sm_max) * sm_inv) : 0.f;
+          }
           if (l + 1 < p.L) {  // prefetch next level
             if constexpr (STAGE) load_sample_inputs_smem<T>(slp, swp, (l + 1) * 4 + ks, nx, ny, naw);
             else load_sample_inputs<T>(lp, wp, (l + 1) * 4 + ks, nx, ny, naw);
@@ -1250,6 +1302,11 @@ template <typename T, int D, int P_T, int SPLIT, int MATH>
 int launch_vec_inst(const MsdaParams &p, const VecPlan &plan, cudaStream_t stream) {
   constexpr int G = D * (int)sizeof(T) / 16;
   if constexpr (P_T == 4 && SPLIT == 1 && G >= 4) {
+    if (p.ref_dim != 0) {
+      msda_fwd_vec<T, D, P_T, SPLIT, MATH, false, true><<<dim3(plan.grid, plan.grid_y, 1), kThreads, 0, stream>>>(p);
+      g_launch_count.fetch_add(1, std::memory_order_relaxed);
+      return (int)cudaGetLastError();
+    }
     if (plan.stage_bytes > 0) {
       msda_fwd_vec<T, D, P_T, SPLIT, MATH, true><<<dim3(plan.grid, plan.grid_y, 1), kThreads, plan.stage_bytes, stream>>>(p);
       g_launch_count.fetch_add(1, std::memory_order_relaxed);
@@ -1329,14 +1386,12 @@ int forward_impl(MsdaParams p, int dtype, unsigned flags, void *workspace, size_
   const bool fused = p.ref_dim != 0;
 
   // ---- choose the kernel ----
-  bool vec_ok = !(flags & MSDA_FLAG_FORCE_GENERIC) && !fused && dtype != MSDA_F64 &&
+  bool vec_ok = !(flags & MSDA_FLAG_FORCE_GENERIC) && dtype != MSDA_F64 &&
                 (p.D == 16 || p.D == 32 || p.D == 64) && p.L <= kMaxLevelsSmem &&
                 aligned_to(p.value, 16) && aligned_to(p.out, 16) && ((size_t)p.M * p.D * E) % 16 == 0;
   const int G = vec_ok ? (int)(p.D * E / 16) : 1;
-  if (vec_ok && p.P == 4) {
-    // the P=4 path reads a level's 4 locations / weights with vector loads
-    vec_ok = aligned_to(p.loc, 16) && aligned_to(p.weight, E == 2 ? 8 : 16);
-  }
+  // the fused-producer mode lives on the broadcast path only (P = 4, rows of at least four lanes)
+  if (fused && !(p.P == 4 && G >= 4)) vec_ok = false;
 
   if (!vec_ok) return run_generic(p, dtype, stream);
 
@@ -1348,8 +1403,8 @@ int forward_impl(MsdaParams p, int dtype, unsigned flags, void *workspace, size_
   // SMs the un-split kernel wins (measured: R50 encoder 608x608 28 us un-split vs 51 us split).
   const int64_t ctas_unsplit = (pairs * G + kThreads - 1) / kThreads;
   plan.split = 1;
-  if (ctas_unsplit < sms && p.P == 4) plan.split = (G * 4 <= 32) ? 4 : ((G * 2 <= 32) ? 2 : 1);
-  plan.split = env_int("MSDA_B200_SPLIT", plan.split);
+  if (ctas_unsplit < sms && p.P == 4 && !fused) plan.split = (G * 4 <= 32) ? 4 : ((G * 2 <= 32) ? 2 : 1);
+  if (!fused) plan.split = env_int("MSDA_B200_SPLIT", plan.split);
   if (!((plan.split == 4 && G * 4 <= 32) || (plan.split == 2 && G * 2 <= 32 && p.P == 4))) plan.split = 1;
 
   // fp16 defaults to the FHFMA path (combined weights rounded to fp16: measured max-normalised error
@@ -1399,7 +1454,7 @@ int forward_impl(MsdaParams p, int dtype, unsigned flags, void *workspace, size_
   plan.stage_bytes = 0;
   p.stage_loc_row = p.stage_w_row = 0;
   const bool want_stage = ((flags & MSDA_FLAG_STAGE_TMA) || env_int("MSDA_B200_STAGE", 0)) && !(flags & MSDA_FLAG_NO_STAGING);
-  if (p.qpp > 0 && p.P == 4 && plan.split == 1 && G >= 4 && want_stage) {
+  if (p.qpp > 0 && p.P == 4 && plan.split == 1 && G >= 4 && want_stage && !fused) {
     const size_t loc_row = (size_t)p.M * p.L * p.P * 2 * E, w_row = (size_t)p.M * p.L * p.P * E;
     auto pad_row = [](size_t bytes) {  // row pitch = 4 (mod 8) words: the 8 lane groups of a warp hit distinct banks
       size_t r = bytes;
@@ -1434,7 +1489,7 @@ int forward_impl(MsdaParams p, int dtype, unsigned flags, void *workspace, size_
   // ---- packed path: pixel-pair packed pyramid in the caller's workspace + 256-bit loads ----
   const size_t packed_need = packed_workspace_bytes(p.B, p.S, p.M, p.D, p.Q, p.L, p.P, dtype);
   const bool packed_ok = packed_need > 0 && workspace != nullptr && workspace_bytes >= packed_need && aligned_to(workspace, 128) &&
-                         plan.split == 1 && !(flags & MSDA_FLAG_NO_PACKED) && env_int("MSDA_B200_PACKED", 1) &&
+                         plan.split == 1 && !fused && !(flags & MSDA_FLAG_NO_PACKED) && env_int("MSDA_B200_PACKED", 1) &&
                          aligned_to(p.loc, 4) && aligned_to(p.weight, 2);
   if (packed_ok) {
     p.packed = workspace;
@@ -1473,7 +1528,7 @@ int forward_impl(MsdaParams p, int dtype, unsigned flags, void *workspace, size_
     snprintf(g_last_variant, sizeof(g_last_variant), "vec<%s,D%d,P%d,split%d>/%s%dx%d/%s/%s%s", dtype_name(dtype), p.D,
              p.P == 4 ? 4 : 0, plan.split, p.want_tiled ? "tiled" : "linear", 1 << p.tile_w_log2, 1 << p.tile_h_log2,
              p.head_major ? "head-major" : "query-major", plan.math == kFhfma ? "fhfma" : "exact",
-             plan.stage_bytes ? "/tma-staged" : "");
+             fused ? "/fused-producers" : (plan.stage_bytes ? "/tma-staged" : ""));
   }
   return rc;
 }

@@ -153,7 +153,7 @@ def main():
             cfgs = [c for c in split_cfgs if "fhfma" not in c["name"]] + [{"name": "default", "flags": 0}]
             have_ref = False
         if args.only == "headline":
-            cfgs = [c for c in cfgs if c["name"] in ("default", "fhfma", "linear+fhfma", "query-major", "tile8x8+fhfma", "tile16x4+fhfma",
+            cfgs = [c for c in cfgs if c["name"] in ("default", "exact-placeholder", "tile8x8+fhfma", "tile16x4+fhfma",
                                                       "tile4x4+fhfma", "split1", "split4", "split1+fhfma", "packed", "packed+exact", "nopacked+exact", "staged")]
             have_ref = False
         ref32 = None
@@ -182,6 +182,23 @@ def main():
             print(f"{name:24s} b{batch} {dtn:8s} {row['loc_mode']:8s} {cfg['name']:20s} {us:9.2f} us  hbm {row['hbm_GBps']:7.1f} GB/s  "
                   f"gather {row['gather_GBps']:8.1f} GB/s  err {row.get('max_rel_vs_fp32', 0):.2e}  {row['variant']}", flush=True)
         set_env({})
+        # opt-in fused-producer entry (softmax + location arithmetic in-kernel) on the same shapes
+        if wl.kind in ("encoder", "decoder") and loc_mode is None:
+            inp = W.make_inputs(wl, batch=batch, seed=wl.seed)
+            cast = lambda a: torch.from_numpy(a).to(device=dev, dtype=dt)
+            refp, off, lg = cast(inp.reference_points), cast(inp.sampling_offsets), cast(inp.attn_logits)
+            s0 = sets[0]
+            outf = torch.empty((batch, wl.Q, wl.num_heads * wl.channels), dtype=dt, device=dev)
+            lib = cb._native.load()
+            fargs = (s0["value"].data_ptr(), s0["spatial_shapes"].data_ptr(), s0["level_start_index"].data_ptr(), refp.data_ptr(),
+                     off.data_ptr(), lg.data_ptr(), outf.data_ptr(), batch, wl.S, wl.num_heads, wl.channels, wl.L, wl.Q,
+                     wl.num_points, refp.shape[-1], cb.ops._DTYPES[dt], 0)
+            stream = torch.cuda.current_stream().cuda_stream
+            us = time_calls([lambda: lib.msda_b200_forward_fused(*fargs, stream)], iters)
+            row = {"workload": name, "batch": batch, "dtype": dtn, "loc_mode": wl.kind, "config": "fused-producers",
+                   "variant": cb.last_variant(), "us_per_call": us, "images_per_s": batch / (us * 1e-6)}
+            results["rows"].append(row)
+            print(f"{name:24s} b{batch} {dtn:8s} {wl.kind:8s} {'fused-producers':20s} {us:9.2f} us  (L2-warm single input set)  {row['variant']}", flush=True)
         if have_ref and dtn in ("float16", "float32"):
             fns = [(lambda s=s: torch.ops.codetr_ref.multi_scale_deformable_attention(*(s[k] for k in KEYS), 64)) for s in sets]
             us = time_calls(fns, max(20, iters // 2))

@@ -313,25 +313,47 @@ def test_host_forward_end_to_end(cuda_device):
     assert d2h == out.numel() * 4 and h2d > d2h
 
 
+def _module_producers(spatial_shapes, reference_points, sampling_offsets, attn_logits, num_points):
+    """The calling module's own PyTorch ops, in the tensors' dtype
+    (codetr/multi_scale_deformable_attention.py:180-200)."""
+    bs, nq, heads, levels, points, _ = sampling_offsets.shape
+    w = attn_logits.reshape(bs, nq, heads, levels * points).softmax(-1).view(bs, nq, heads, levels, points)
+    if reference_points.shape[-1] == 2:
+        norm = torch.stack([spatial_shapes[..., 1], spatial_shapes[..., 0]], -1)
+        loc = reference_points[:, :, None, :, None, :] + sampling_offsets / norm[None, None, None, :, None, :]
+    else:
+        loc = reference_points[:, :, None, :, None, :2] + sampling_offsets / num_points * reference_points[:, :, None, :, None, 2:] * 0.5
+    return loc.contiguous(), w.contiguous()
+
+
+@pytest.mark.parametrize("flags", [0, cb.FLAG_FORCE_GENERIC], ids=["vector", "generic"])
 @pytest.mark.parametrize("kind,q", [("encoder", 0), ("decoder", 37)])
-@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
-def test_fused_producers(kind, q, dtype, cuda_device):
-    """Opt-in fused entry: softmax + sampling-location arithmetic inside the kernel, checked against
-    oracle producers -> oracle forward."""
-    wl = W.Workload(name="t", shapes=tuple(W.pyramid_shapes(64, 96)), num_queries=q, batch=2, kind=kind, seed=5)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+def test_fused_producers(kind, q, dtype, flags, cuda_device):
+    """Opt-in fused entry (softmax + sampling-location arithmetic inside the kernel) against the unfused
+    pipeline: the module's PyTorch ops in the tensor dtype, then the fp32 reference of the op."""
+    wl = W.Workload(name="t", shapes=tuple(W.pyramid_shapes(128, 192)), num_queries=q, batch=2, kind=kind, seed=5)
     inp = W.make_inputs(wl)
     dev = lambda a: torch.from_numpy(a).to(cuda_device)
     cast = lambda a: dev(a).to(dtype)
     ref_pts, off, lg = cast(inp.reference_points), cast(inp.sampling_offsets), cast(inp.attn_logits)
-    value = cast(inp.value)
-    out = cb.forward_fused(value, dev(inp.spatial_shapes), dev(inp.level_start_index), ref_pts, off, lg)
-    loc, w = oracle.producers_c(inp.spatial_shapes, ref_pts.float().cpu().numpy(), off.float().cpu().numpy(),
-                                lg.float().cpu().numpy())
-    ref = oracle.forward_c(value.float().cpu().numpy(), inp.spatial_shapes, inp.level_start_index, loc, w)
+    value, shapes, starts = cast(inp.value), dev(inp.spatial_shapes), dev(inp.level_start_index)
+    out = cb.forward_fused(value, shapes, starts, ref_pts, off, lg, flags=flags)
+    assert ("fused" in cb.last_variant()) and cb.last_variant().startswith("generic" if flags else "vec<")
+    loc, w = _module_producers(shapes, ref_pts, off, lg, wl.num_points)
+    assert loc.dtype == dtype and w.dtype == dtype
+    ref = oracle.forward_c(value.float().cpu().numpy(), inp.spatial_shapes, inp.level_start_index,
+                           loc.float().cpu().numpy(), w.float().cpu().numpy())
+    got = out.float().cpu().numpy()
     if dtype == torch.float32:
-        assert rel_l2(out.cpu().numpy(), ref) <= FP32_REL_L2
+        assert rel_l2(got, ref) <= FP32_REL_L2
     else:
-        assert max_rel(out.float().cpu().numpy(), ref) <= HALF_MAX_REL
+        # the kernel rounds its intermediates where the PyTorch ops do; what is left is an occasional
+        # 1-ulp difference of a softmax weight or a location, well inside the gate
+        assert max_rel(got, ref) <= (HALF_MAX_REL if dtype == torch.float16 else 2 * BF16_MAX_REL)
+    # and it agrees with this library's own unfused op on those PyTorch-made inputs
+    unfused = cb.multi_scale_deformable_attention(value, shapes, starts, loc, w, flags=flags)
+    assert max_rel(got, unfused.float().cpu().numpy()) <= (1e-5 if dtype == torch.float32 else 2 * (HALF_MAX_REL if dtype == torch.float16 else BF16_MAX_REL))
 
 
 # ----------------------------------------------------------------------------------------------
