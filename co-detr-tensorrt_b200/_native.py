@@ -39,6 +39,7 @@ EXPORTED_SYMBOLS = [
     "msda_b200_plugin_workspace_bytes",
     "msda_b200_plugin_enqueue",
     "msda_b200_forward_fused",
+    "msda_b200_backward",
     "msda_b200_host_workspace_bytes",
     "msda_b200_forward_host",
     "msda_b200_abi_version",
@@ -131,6 +132,8 @@ def load() -> ctypes.CDLL:
     lib.msda_b200_workspace_bytes.argtypes = [i64, i64, i64, i64, i64, i64, i64, ci]
     lib.msda_b200_plugin_workspace_bytes.restype = ctypes.c_size_t
     lib.msda_b200_plugin_workspace_bytes.argtypes = [vp, vp, ci]
+    lib.msda_b200_backward.restype = ci
+    lib.msda_b200_backward.argtypes = [vp] * 9 + [i64] * 8 + [ci, cu, vp]
     lib.msda_b200_plugin_enqueue.restype = ci
     lib.msda_b200_plugin_enqueue.argtypes = [vp, vp, ci, vp, vp, vp, ctypes.c_size_t, i64, vp]
     lib.msda_b200_host_workspace_bytes.restype = ctypes.c_size_t

@@ -85,13 +85,40 @@ at::Tensor ms_deform_attn_forward(const at::Tensor &value, const at::Tensor &spa
   return output;
 }
 
-// The backward pass (ms_deform_attn.cu:975-1028) is outside this repo's scope (BASELINE.json north_star:
-// forward core).  The symbol exists so that the reference's torch binding links
-// unchanged; calling it fails loudly instead of silently returning zero gradients.
-void ms_deform_attn_backward(const at::Tensor &, const at::Tensor &, const at::Tensor &, const at::Tensor &,
-                             const at::Tensor &, const at::Tensor &, at::Tensor &, at::Tensor &, at::Tensor &,
-                             const int64_t) {
-  TORCH_CHECK(false, "codetr::ms_deform_attn_backward is not provided by the B200 forward-only build");
+// Backward (ms_deform_attn.cu:975-1028): same asserts, then the C ABI.  grad_value is accumulated into
+// (the reference's autograd glue passes zeros, codetr/ops.py:94-96), the other two are overwritten.
+void ms_deform_attn_backward(const at::Tensor &value, const at::Tensor &spatial_shapes, const at::Tensor &level_start_index,
+                             const at::Tensor &sampling_loc, const at::Tensor &attn_weight, const at::Tensor &grad_output,
+                             at::Tensor &grad_value, at::Tensor &grad_sampling_loc, at::Tensor &grad_attn_weight,
+                             const int64_t im2col_step) {
+  TORCH_CHECK(value.is_contiguous(), "value tensor has to be contiguous");
+  TORCH_CHECK(spatial_shapes.is_contiguous(), "spatial_shapes tensor has to be contiguous");
+  TORCH_CHECK(level_start_index.is_contiguous(), "level_start_index tensor has to be contiguous");
+  TORCH_CHECK(sampling_loc.is_contiguous(), "sampling_loc tensor has to be contiguous");
+  TORCH_CHECK(attn_weight.is_contiguous(), "attn_weight tensor has to be contiguous");
+  TORCH_CHECK(grad_output.is_contiguous(), "grad_output tensor has to be contiguous");
+  TORCH_CHECK(grad_value.is_contiguous() && grad_sampling_loc.is_contiguous() && grad_attn_weight.is_contiguous(),
+              "gradient tensors have to be contiguous");
+  TORCH_CHECK(value.is_cuda() && spatial_shapes.is_cuda() && level_start_index.is_cuda() && sampling_loc.is_cuda() &&
+                  attn_weight.is_cuda() && grad_output.is_cuda() && grad_value.is_cuda() && grad_sampling_loc.is_cuda() &&
+                  grad_attn_weight.is_cuda(),
+              "all tensors must be CUDA tensors");
+  TORCH_CHECK(value.dim() == 4 && sampling_loc.dim() == 6 && spatial_shapes.dim() == 2, "unexpected tensor ranks");
+  const auto st = value.scalar_type();
+  TORCH_CHECK(sampling_loc.scalar_type() == st && attn_weight.scalar_type() == st && grad_output.scalar_type() == st &&
+                  grad_value.scalar_type() == st && grad_sampling_loc.scalar_type() == st && grad_attn_weight.scalar_type() == st,
+              "all floating tensors must share one dtype");
+  TORCH_CHECK(grad_value.sizes() == value.sizes() && grad_sampling_loc.sizes() == sampling_loc.sizes() &&
+                  grad_attn_weight.sizes() == attn_weight.sizes(),
+              "gradient shapes must match their tensors");
+  const c10::cuda::CUDAGuard device_guard(value.device());
+  cudaStream_t stream = at::cuda::getCurrentCUDAStream();
+  const int rc = msda_b200_backward(value.data_ptr(), spatial_shapes.data_ptr<int64_t>(), level_start_index.data_ptr<int64_t>(),
+                                    sampling_loc.data_ptr(), attn_weight.data_ptr(), grad_output.data_ptr(), grad_value.data_ptr(),
+                                    grad_sampling_loc.data_ptr(), grad_attn_weight.data_ptr(), value.size(0), value.size(1),
+                                    value.size(2), value.size(3), spatial_shapes.size(0), sampling_loc.size(1),
+                                    sampling_loc.size(4), im2col_step, to_msda_dtype(st), MSDA_FLAG_DEFAULT, stream);
+  TORCH_CHECK(rc == 0, "ms_deform_attn_backward: ", msda_b200_error_string(rc));
 }
 
 } // namespace codetr

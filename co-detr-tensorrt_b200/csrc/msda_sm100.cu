@@ -152,12 +152,17 @@ __device__ __forceinline__ float floor_acc<float>(float v) { return floorf(v); }
 template <>
 __device__ __forceinline__ double floor_acc<double>(double v) { return floor(v); }
 
+// product rounded on its own (never contracted into an FMA with the following subtraction), like the
+// reference's scalar_t arithmetic `loc * size - 0.5`: at exact-integer pixel coordinates the choice of the
+// bilinear cell -- and with it the one-sided derivative the backward returns -- depends on this rounding
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+
 template <typename A>
 __device__ __forceinline__ Sample<A> make_sample(A x, A y, A aw, int H, int W) {
   Sample<A> s;
-  // x*W - 0.5 with the product rounded first, like the reference's scalar_t arithmetic
-  const A w_im = x * (A)W - (A)0.5;
-  const A h_im = y * (A)H - (A)0.5;
+  const A w_im = mul_rn(x, (A)W) - (A)0.5;
+  const A h_im = mul_rn(y, (A)H) - (A)0.5;
   const bool inside = (h_im > (A)-1) && (w_im > (A)-1) && (h_im < (A)H) && (w_im < (A)W);
   const A hf = floor_acc<A>(h_im), wf = floor_acc<A>(w_im);
   const int h_lo = inside ? (int)hf : 0;
@@ -1221,6 +1226,231 @@ __global__ void __launch_bounds__(kThreads, MSDA_MINB) msda_fwd_packed(const Msd
 }
 
 // ---------------------------------------------------------------------------
+// Backward: gradients w.r.t. value (scatter-add with atomics, like the
+// reference), sampling locations and attention weights.  Per-sample derivative of
+// ms_deform_attn.cu:79-141; the reference's six kernel variants (:263-760) differ only in how the
+// per-channel partial sums are reduced -- here a lane group owns a (query, head) pair, each lane holds
+// D/G channels, and the four corner dot products are reduced over the group with shuffles.
+//   grad_value   accumulated into the caller's zero-initialised buffer (codetr/ops.py:94-96)
+//   grad_loc, grad_weight   fully overwritten
+// ---------------------------------------------------------------------------
+struct BwdParams {
+  const void *value;
+  const int64_t *shapes;
+  const int64_t *starts;
+  const void *loc;
+  const void *weight;
+  const void *grad_out;
+  void *grad_value;
+  void *grad_loc;
+  void *grad_weight;
+  int B, S, M, D, L, Q, P;
+};
+
+template <typename T>
+__device__ __forceinline__ void atomic_add_elem(T *addr, typename Elem<T>::acc_t v) {
+  atomicAdd(addr, Elem<T>::from_acc(v));
+}
+
+// geometry of one sample for the backward: corner indices, validity, weights and their derivatives
+template <typename A>
+struct BwdSample {
+  int idx[4];
+  bool ok[4];
+  A cw[4], dh[4], dw[4];
+  bool inside;
+};
+
+template <typename A>
+__device__ __forceinline__ BwdSample<A> make_bwd_sample(A x, A y, int H, int W) {
+  BwdSample<A> s;
+  const A w_im = mul_rn(x, (A)W) - (A)0.5;
+  const A h_im = mul_rn(y, (A)H) - (A)0.5;
+  s.inside = (h_im > (A)-1) && (w_im > (A)-1) && (h_im < (A)H) && (w_im < (A)W);
+  const A hf = floor_acc<A>(h_im), wf = floor_acc<A>(w_im);
+  const int h_lo = s.inside ? (int)hf : 0, w_lo = s.inside ? (int)wf : 0;
+  const A lh = h_im - hf, lw = w_im - wf, hh = (A)1 - lh, hw = (A)1 - lw;
+  const bool top = h_lo >= 0, bot = h_lo + 1 <= H - 1, lef = w_lo >= 0, rig = w_lo + 1 <= W - 1;
+  s.ok[0] = s.inside && top && lef;
+  s.ok[1] = s.inside && top && rig;
+  s.ok[2] = s.inside && bot && lef;
+  s.ok[3] = s.inside && bot && rig;
+  const int base = h_lo * W + w_lo;
+  s.idx[0] = base;
+  s.idx[1] = base + 1;
+  s.idx[2] = base + W;
+  s.idx[3] = base + W + 1;
+  s.cw[0] = hh * hw; s.cw[1] = hh * lw; s.cw[2] = lh * hw; s.cw[3] = lh * lw;
+  s.dh[0] = -hw; s.dh[1] = -lw; s.dh[2] = hw; s.dh[3] = lw;    // d cw / d h_im
+  s.dw[0] = -hh; s.dw[1] = hh; s.dw[2] = -lh; s.dw[3] = lh;    // d cw / d w_im
+  return s;
+}
+
+// Generic backward: one thread per (pair, sample), serial over the D channels.  Any shape, any dtype.
+template <typename T>
+__global__ void __launch_bounds__(kThreads) msda_bwd_generic(const BwdParams p) {
+  using A = typename Elem<T>::acc_t;
+  const T *__restrict__ value = static_cast<const T *>(p.value);
+  const T *__restrict__ loc = static_cast<const T *>(p.loc);
+  const T *__restrict__ wgt = static_cast<const T *>(p.weight);
+  const T *__restrict__ go = static_cast<const T *>(p.grad_out);
+  T *gv = static_cast<T *>(p.grad_value);
+  T *gl = static_cast<T *>(p.grad_loc);
+  T *gw = static_cast<T *>(p.grad_weight);
+  const int LP = p.L * p.P;
+  const int64_t n = (int64_t)p.B * p.Q * p.M * LP;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int lp = (int)(i % LP);
+    const int64_t pair = i / LP;
+    const int l = lp / p.P;
+    const int m = (int)(pair % p.M);
+    const int64_t b = pair / p.M / p.Q;
+    const int H = (int)p.shapes[2 * l], W = (int)p.shapes[2 * l + 1];
+    const int64_t lvl = ((int64_t)b * p.S + p.starts[l]) * p.M * p.D + (int64_t)m * p.D;
+    const A aw = Elem<T>::to_acc(wgt[i]);
+    const BwdSample<A> s = make_bwd_sample<A>(Elem<T>::to_acc(loc[i * 2]), Elem<T>::to_acc(loc[i * 2 + 1]), H, W);
+    A g_x = 0, g_y = 0, g_w = 0;
+    if (s.inside) {
+      for (int c = 0; c < p.D; ++c) {
+        const A tg = Elem<T>::to_acc(go[pair * p.D + c]);
+        const A tgv = tg * aw;
+        A val = 0, gh = 0, gwd = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (!s.ok[j]) continue;
+          const int64_t off = lvl + (int64_t)s.idx[j] * p.M * p.D + c;
+          const A v = Elem<T>::to_acc(value[off]);
+          val += s.cw[j] * v;
+          gh += s.dh[j] * v;
+          gwd += s.dw[j] * v;
+          atomic_add_elem<T>(gv + off, s.cw[j] * tgv);
+        }
+        g_w += tg * val;
+        g_x += (A)W * gwd * tgv;
+        g_y += (A)H * gh * tgv;
+      }
+    }
+    gl[i * 2] = Elem<T>::from_acc(g_x);
+    gl[i * 2 + 1] = Elem<T>::from_acc(g_y);
+    gw[i] = Elem<T>::from_acc(g_w);
+  }
+}
+
+// 16-byte vector reduction into grad_value (REDG.E.ADD.F16x8 / BF16x8 / F32x4 on sm_100a)
+template <typename T>
+__device__ __forceinline__ void red_add_row(void *addr, const float *v);
+template <>
+__device__ __forceinline__ void red_add_row<float>(void *addr, const float *v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(addr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+}
+template <>
+__device__ __forceinline__ void red_add_row<__half>(void *addr, const float *v) {
+  asm volatile("red.global.add.noftz.v4.f16x2 [%0], {%1,%2,%3,%4};" ::"l"(addr), "r"(pack_weights<__half>(v[0], v[1])),
+               "r"(pack_weights<__half>(v[2], v[3])), "r"(pack_weights<__half>(v[4], v[5])), "r"(pack_weights<__half>(v[6], v[7]))
+               : "memory");
+}
+template <>
+__device__ __forceinline__ void red_add_row<__nv_bfloat16>(void *addr, const float *v) {
+  asm volatile("red.global.add.noftz.v4.bf16x2 [%0], {%1,%2,%3,%4};" ::"l"(addr), "r"(pack_weights<__nv_bfloat16>(v[0], v[1])),
+               "r"(pack_weights<__nv_bfloat16>(v[2], v[3])), "r"(pack_weights<__nv_bfloat16>(v[4], v[5])),
+               "r"(pack_weights<__nv_bfloat16>(v[6], v[7]))
+               : "memory");
+}
+
+template <typename T, int VEC>
+__device__ __forceinline__ void unpack_row(const uint4 &r, float (&f)[VEC]) {
+  if constexpr (sizeof(T) == 4) {
+    f[0] = __uint_as_float(r.x); f[1] = __uint_as_float(r.y); f[2] = __uint_as_float(r.z); f[3] = __uint_as_float(r.w);
+  } else {
+    const unsigned w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 t = unpack2<T>(w[i]);
+      f[2 * i] = t.x;
+      f[2 * i + 1] = t.y;
+    }
+  }
+}
+
+// Vector backward: lane group of G = D*sizeof(T)/16 lanes per (query, head) pair.
+template <typename T, int D>
+__global__ void __launch_bounds__(kThreads) msda_bwd_vec(const BwdParams p) {
+  constexpr int E = (int)sizeof(T), VEC = 16 / E, G = D / VEC, PAIRS_PER_CTA = kThreads / G;
+  const char *__restrict__ value = static_cast<const char *>(p.value);
+  const T *__restrict__ loc = static_cast<const T *>(p.loc);
+  const T *__restrict__ wgt = static_cast<const T *>(p.weight);
+  const char *__restrict__ go = static_cast<const char *>(p.grad_out);
+  char *gv = static_cast<char *>(p.grad_value);
+  T *gl = static_cast<T *>(p.grad_loc);
+  T *gw = static_cast<T *>(p.grad_weight);
+  const int LP = p.L * p.P;
+  const int sub = threadIdx.x % G;
+  const size_t pix_bytes = (size_t)p.M * D * E;
+  const int64_t pairs = (int64_t)p.B * p.Q * p.M;
+  // every lane of a warp runs the same trip count (dead pairs carry zero grad_out), so the group
+  // reductions below can use the full mask
+  const int64_t trips = (pairs + (int64_t)gridDim.x * PAIRS_PER_CTA - 1) / ((int64_t)gridDim.x * PAIRS_PER_CTA);
+  for (int64_t tr = 0; tr < trips; ++tr) {
+    const int64_t pr = (tr * gridDim.x + blockIdx.x) * PAIRS_PER_CTA + threadIdx.x / G;
+    const bool live = pr < pairs;
+    const int64_t pair = live ? pr : 0;
+    const int m = (int)(pair % p.M);
+    const int64_t b = pair / p.M / p.Q;
+    float g[VEC];
+    {
+      uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+      if (live) raw = ldg128(go + (size_t)pair * D * E + (size_t)sub * 16);
+      unpack_row<T, VEC>(raw, g);
+    }
+    for (int l = 0; l < p.L; ++l) {
+      const int H = (int)__ldg(p.shapes + 2 * l), W = (int)__ldg(p.shapes + 2 * l + 1);
+      const size_t lvl = (((size_t)b * p.S + (size_t)__ldg(p.starts + l)) * p.M + m) * (size_t)(D * E) + (size_t)sub * 16;
+      for (int k = 0; k < p.P; ++k) {
+        const int64_t si = pair * LP + (int64_t)l * p.P + k;
+        float x, y, aw;
+        load_sample_inputs<T>(loc + pair * LP * 2, wgt + pair * LP, l * p.P + k, x, y, aw);
+        const BwdSample<float> s = make_bwd_sample<float>(x, y, H, W);
+        float t[4];  // per-corner dot product of grad_out with the value row (this lane's channels)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          t[j] = 0.f;
+          if (s.ok[j]) {
+            const size_t off = lvl + (size_t)(unsigned)s.idx[j] * pix_bytes;
+            float v[VEC];
+            unpack_row<T, VEC>(ldg128(value + off), v);
+            float dv[VEC];
+#pragma unroll
+            for (int c = 0; c < VEC; ++c) {
+              t[j] = fmaf(g[c], v[c], t[j]);
+              dv[c] = s.cw[j] * aw * g[c];
+            }
+            if (live) red_add_row<T>(gv + off, dv);
+          }
+        }
+#pragma unroll
+        for (int off = 1; off < G; off <<= 1) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) t[j] += __shfl_xor_sync(0xffffffffu, t[j], off);
+        }
+        if (live && sub == 0) {
+          float val = 0.f, gh = 0.f, gwd = 0.f;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            val = fmaf(s.cw[j], t[j], val);
+            gh = fmaf(s.dh[j], t[j], gh);
+            gwd = fmaf(s.dw[j], t[j], gwd);
+          }
+          // samples outside the range test have all-zero t[] (no corner was read): gradients are zero
+          gl[si * 2] = Elem<T>::from_acc(s.inside ? (float)W * gwd * aw : 0.f);
+          gl[si * 2 + 1] = Elem<T>::from_acc(s.inside ? (float)H * gh * aw : 0.f);
+          gw[si] = Elem<T>::from_acc(s.inside ? val : 0.f);
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // read-bandwidth probe (roofline denominators: L2 -> SM, HBM -> SM)
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) read_probe_kernel(const uint4 *__restrict__ buf, size_t n_vec, int repeats,
@@ -1748,6 +1978,69 @@ int msda_b200_forward_host(const void *value_host, const int64_t *spatial_shapes
   MSDA_COPY(output_host, d_out, n_out, cudaMemcpyDeviceToHost)
 #undef MSDA_COPY
   return MSDA_OK;
+}
+
+int msda_b200_backward(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                       const void *sampling_loc, const void *attn_weight, const void *grad_output, void *grad_value,
+                       void *grad_sampling_loc, void *grad_attn_weight, int64_t batch, int64_t num_keys, int64_t num_heads,
+                       int64_t channels, int64_t num_levels, int64_t num_queries, int64_t num_points, int64_t im2col_step,
+                       int dtype, unsigned flags, void *stream_v) {
+  const size_t E = elem_size(dtype);
+  if (E == 0) return MSDA_ERR_BAD_DTYPE;
+  if (batch < 0 || num_keys < 0 || num_heads < 0 || channels < 0 || num_levels < 0 || num_queries < 0 || num_points < 0)
+    return MSDA_ERR_BAD_SHAPE;
+  const int64_t lim = (int64_t)1 << 31;
+  if (num_keys >= lim || num_queries >= lim || batch >= lim || num_heads >= 65536 || channels >= 65536 || num_levels >= 65536 ||
+      num_points >= 65536)
+    return MSDA_ERR_UNSUPPORTED;
+  if (batch > 0) {  // ms_deform_attn.cu:999-1001
+    const int64_t step = batch < im2col_step ? batch : im2col_step;
+    if (step <= 0 || batch % step != 0) return MSDA_ERR_BAD_STEP;
+  }
+  const int64_t samples = batch * num_queries * num_heads * num_levels * num_points;
+  if (samples == 0) return MSDA_OK;
+  if (!value || !spatial_shapes || !level_start_index || !sampling_loc || !attn_weight || !grad_output || !grad_value ||
+      !grad_sampling_loc || !grad_attn_weight)
+    return MSDA_ERR_NULL_POINTER;
+  const void *ptrs[] = {value, sampling_loc, attn_weight, grad_output, grad_value, grad_sampling_loc, grad_attn_weight};
+  for (const void *q : ptrs)
+    if (!aligned_to(q, E)) return MSDA_ERR_MISALIGNED;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  BwdParams p;
+  p.value = value; p.shapes = spatial_shapes; p.starts = level_start_index; p.loc = sampling_loc; p.weight = attn_weight;
+  p.grad_out = grad_output; p.grad_value = grad_value; p.grad_loc = grad_sampling_loc; p.grad_weight = grad_attn_weight;
+  p.B = (int)batch; p.S = (int)num_keys; p.M = (int)num_heads; p.D = (int)channels; p.L = (int)num_levels;
+  p.Q = (int)num_queries; p.P = (int)num_points;
+  const int sms = sm_count();
+  const bool vec = !(flags & MSDA_FLAG_FORCE_GENERIC) && dtype != MSDA_F64 &&
+                   ((E == 2 && channels == 32) || (E == 4 && (channels == 16 || channels == 32))) &&
+                   aligned_to(value, 16) && aligned_to(grad_output, 16) && aligned_to(grad_value, 16) &&
+                   aligned_to(sampling_loc, 2 * E) && ((size_t)num_heads * channels * E) % 16 == 0;
+  if (vec) {
+    const int G = (int)(channels * E / 16);
+    const int64_t pairs = batch * num_queries * num_heads;
+    int64_t grid = (pairs * G + kThreads - 1) / kThreads;
+    const int64_t cap = (int64_t)sms * 32;
+    if (grid > cap) grid = cap;
+    if (dtype == MSDA_F16) msda_bwd_vec<__half, 32><<<(unsigned)grid, kThreads, 0, stream>>>(p);
+    else if (dtype == MSDA_BF16) msda_bwd_vec<__nv_bfloat16, 32><<<(unsigned)grid, kThreads, 0, stream>>>(p);
+    else if (channels == 16) msda_bwd_vec<float, 16><<<(unsigned)grid, kThreads, 0, stream>>>(p);
+    else msda_bwd_vec<float, 32><<<(unsigned)grid, kThreads, 0, stream>>>(p);
+    snprintf(g_last_variant, sizeof(g_last_variant), "bwd_vec<%s,D%d>", dtype_name(dtype), (int)channels);
+  } else {
+    int64_t grid = (samples + kThreads - 1) / kThreads;
+    const int64_t cap = (int64_t)sms * 32;
+    if (grid > cap) grid = cap;
+    switch (dtype) {
+      case MSDA_F32: msda_bwd_generic<float><<<(unsigned)grid, kThreads, 0, stream>>>(p); break;
+      case MSDA_F16: msda_bwd_generic<__half><<<(unsigned)grid, kThreads, 0, stream>>>(p); break;
+      case MSDA_BF16: msda_bwd_generic<__nv_bfloat16><<<(unsigned)grid, kThreads, 0, stream>>>(p); break;
+      default: msda_bwd_generic<double><<<(unsigned)grid, kThreads, 0, stream>>>(p); break;
+    }
+    snprintf(g_last_variant, sizeof(g_last_variant), "bwd_generic<%s>", dtype_name(dtype));
+  }
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  return (int)cudaGetLastError();
 }
 
 int msda_b200_read_probe(const void *buf, size_t bytes, int repeats, void *sink, void *stream) {

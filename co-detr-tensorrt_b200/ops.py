@@ -31,6 +31,11 @@ from . import _native
 
 _lib = _native.load()
 
+BACKWARD_SCHEMA = (
+    "multi_scale_deformable_attention_backward(Tensor value, Tensor spatial_shapes, Tensor level_start_index, "
+    "Tensor sampling_loc, Tensor attn_weight, Tensor grad_output, Tensor(a!) grad_value, "
+    "Tensor(b!) grad_sampling_loc, Tensor(c!) grad_attn_weight, int im2col_step) -> ()"
+)
 OP_SCHEMA = (
     "multi_scale_deformable_attention(Tensor value, Tensor spatial_shapes, "
     "Tensor level_start_index, Tensor sampling_loc, Tensor attn_weight, "
@@ -177,6 +182,42 @@ def multi_scale_deformable_attention(
             ws = torch.empty(need, dtype=torch.uint8, device=value.device)  # torch's caching allocator: no cudaMalloc in steady state
     return forward_into(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, out, im2col_step, flags,
                         workspace=ws)
+
+
+def backward_into(
+    value: Tensor,
+    spatial_shapes: Tensor,
+    level_start_index: Tensor,
+    sampling_loc: Tensor,
+    attn_weight: Tensor,
+    grad_output: Tensor,
+    grad_value: Tensor,
+    grad_sampling_loc: Tensor,
+    grad_attn_weight: Tensor,
+    im2col_step: int = 64,
+    flags: Optional[int] = None,
+) -> None:
+    """``codetr::ms_deform_attn_backward`` (ms_deform_attn.cu:975-1028): accumulates into ``grad_value``
+    (zero it first, as codetr/ops.py:94-96 does), overwrites the other two gradients."""
+    _validate(value, spatial_shapes, level_start_index, sampling_loc, attn_weight)
+    bs, keys, heads, chans = value.shape
+    queries, levels, points = sampling_loc.shape[1], sampling_loc.shape[3], sampling_loc.shape[4]
+    for name, t, like in (("grad_output", grad_output, None), ("grad_value", grad_value, value),
+                          ("grad_sampling_loc", grad_sampling_loc, sampling_loc), ("grad_attn_weight", grad_attn_weight, attn_weight)):
+        _require(t.is_contiguous(), f"{name} tensor has to be contiguous")
+        _require(t.is_cuda and t.device == value.device, f"{name} must be a CUDA tensor on value's device")
+        _require(t.dtype == value.dtype, f"{name} dtype must match value")
+        if like is not None:
+            _require(tuple(t.shape) == tuple(like.shape), f"{name} shape mismatch")
+    _require(tuple(grad_output.shape) == (bs, queries, heads * chans), "grad_output must be [bs, num_queries, num_heads*channels]")
+    with torch.cuda.device(value.device):
+        rc = _lib.msda_b200_backward(
+            value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), sampling_loc.data_ptr(),
+            attn_weight.data_ptr(), grad_output.data_ptr(), grad_value.data_ptr(), grad_sampling_loc.data_ptr(),
+            grad_attn_weight.data_ptr(), bs, keys, heads, chans, levels, queries, points, int(im2col_step),
+            _DTYPES[value.dtype], _default_flags if flags is None else int(flags), _stream_ptr(value.device, None),
+        )
+    _check(rc)
 
 
 class PreparedForward:
@@ -434,6 +475,30 @@ def _op_cuda(value, spatial_shapes, level_start_index, sampling_loc, attn_weight
                                             im2col_step)
 
 
+def _op_backward_cuda(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output, grad_value,
+                      grad_sampling_loc, grad_attn_weight, im2col_step):
+    backward_into(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output, grad_value,
+                  grad_sampling_loc, grad_attn_weight, im2col_step)
+
+
+def _autograd_backward(ctx, grad):
+    # same glue as the reference's codetr/ops.py:90-114: zero-filled gradient buffers, one backward op call
+    value, spatial_shapes, level_start_index, sampling_loc, attn_weight = ctx.saved_tensors
+    grad_value = torch.zeros_like(value)
+    grad_loc = torch.empty_like(sampling_loc)
+    grad_w = torch.empty_like(attn_weight)
+    torch.ops.codetr.multi_scale_deformable_attention_backward(
+        value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad.contiguous(), grad_value, grad_loc,
+        grad_w, ctx.im2col_step)
+    return grad_value, None, None, grad_loc, grad_w, None
+
+
+def _autograd_setup(ctx, inputs, output):
+    value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step = inputs
+    ctx.im2col_step = im2col_step
+    ctx.save_for_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight)
+
+
 _torch_lib = None
 
 
@@ -449,8 +514,12 @@ def register_torch_op() -> None:
         return
     lib = torch.library.Library("codetr", "DEF")
     lib.define(OP_SCHEMA)
+    lib.define(BACKWARD_SCHEMA)
     lib.impl("multi_scale_deformable_attention", _op_cuda, "CUDA")
+    lib.impl("multi_scale_deformable_attention_backward", _op_backward_cuda, "CUDA")
     torch.library.register_fake("codetr::multi_scale_deformable_attention", _fake, lib=lib)
+    torch.library.register_autograd("codetr::multi_scale_deformable_attention", _autograd_backward,
+                                    setup_context=_autograd_setup, lib=lib)
     _torch_lib = lib
 
 

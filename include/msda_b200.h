@@ -175,6 +175,23 @@ int msda_b200_forward_host(const void *value_host, const int64_t *spatial_shapes
                            int64_t channels, int64_t num_levels, int64_t num_queries, int64_t num_points,
                            int64_t im2col_step, int dtype, unsigned flags, void *stream);
 
+/*
+ * msda_b200_backward -- gradients of the forward.
+ *
+ * Stands behind  codetr::ms_deform_attn_backward  (codetr/csrc/ms_deform_attn.cu:975-1028; bound to the torch
+ * op codetr::multi_scale_deformable_attention_backward, deformable_attention_torch.cpp:20-23, :30; called
+ * by the autograd glue codetr/ops.py:90-126).  grad_output [B,Q,M*D]; grad_value [B,S,M,D] is ACCUMULATED
+ * into (atomics) and must be zero-initialised by the caller, as the reference's glue does (ops.py:94-96);
+ * grad_sampling_loc [B,Q,M,L,P,2] and grad_attn_weight [B,Q,M,L,P] are fully overwritten.  Per-sample
+ * derivative follows ms_deform_attn.cu:79-141 (arithmetic in fp32 for 16-bit types, fp64 for double).
+ */
+int msda_b200_backward(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                       const void *sampling_loc, const void *attn_weight, const void *grad_output,
+                       void *grad_value, void *grad_sampling_loc, void *grad_attn_weight, int64_t batch,
+                       int64_t num_keys, int64_t num_heads, int64_t channels, int64_t num_levels,
+                       int64_t num_queries, int64_t num_points, int64_t im2col_step, int dtype,
+                       unsigned flags, void *stream);
+
 /* ---- introspection / measurement helpers (no reference counterpart) ---- */
 
 /* ABI version of the loaded library (== MSDA_B200_ABI_VERSION). */

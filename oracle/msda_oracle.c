@@ -165,3 +165,73 @@ DEFINE_ORACLE(msda_oracle_forward_f64, double, floor)
 
 DEFINE_PRODUCERS(msda_oracle_producers_f32, float, expf)
 DEFINE_PRODUCERS(msda_oracle_producers_f64, double, exp)
+
+/*
+ * Backward of the forward above: gradients w.r.t. value (scatter-add), the sampling locations and the
+ * attention weights, given grad_out [B,Q,M*D].  Restates the reference's per-sample derivative
+ *   codetr/csrc/ms_deform_attn.cu:79-141   (ms_deform_attn_col2im_bilinear)
+ * and its caller loop :263-345 (one of six variants that differ only in how the per-channel partial
+ * sums are reduced); the channel reduction here is a plain serial sum.  grad_value must be zeroed by the
+ * caller (the reference's autograd glue passes zeros, codetr/ops.py:94-96); grad_loc and grad_weight are
+ * fully overwritten.  Serial over (b, q, m) so the scatter-add needs no atomics: test infrastructure,
+ * not a performance path.
+ */
+#define DEFINE_ORACLE_BWD(NAME, T, FLOORFN)                                                      \
+  void NAME(const T *value, const int64_t *shapes, const int64_t *starts, const T *loc,          \
+            const T *weight, const T *grad_out, T *grad_value, T *grad_loc, T *grad_weight,      \
+            int64_t B, int64_t S, int64_t M, int64_t D, int64_t L, int64_t Q, int64_t P) {       \
+    const int64_t pix_stride = M * D;                                                            \
+    for (int64_t b = 0; b < B; ++b)                                                              \
+      for (int64_t q = 0; q < Q; ++q)                                                            \
+        for (int64_t m = 0; m < M; ++m) {                                                        \
+          const int64_t qm = (b * Q + q) * M + m;                                                \
+          const T *go = grad_out + qm * D;                                                       \
+          for (int64_t l = 0; l < L; ++l) {                                                      \
+            const int H = (int)shapes[2 * l], W = (int)shapes[2 * l + 1];                        \
+            const int64_t lvl_off = (b * S + starts[l]) * pix_stride + m * D;                    \
+            for (int64_t p = 0; p < P; ++p) {                                                    \
+              const int64_t si = qm * L * P + l * P + p;                                         \
+              const T x = loc[si * 2], y = loc[si * 2 + 1], aw = weight[si];                     \
+              T g_x = (T)0, g_y = (T)0, g_w = (T)0;                                              \
+              const T h_im = y * (T)H - (T)0.5, w_im = x * (T)W - (T)0.5;                        \
+              if (h_im > (T)-1 && w_im > (T)-1 && h_im < (T)H && w_im < (T)W) {                  \
+                const int h_lo = (int)FLOORFN(h_im), w_lo = (int)FLOORFN(w_im);                  \
+                const int h_hi = h_lo + 1, w_hi = w_lo + 1;                                      \
+                const T lh = h_im - (T)h_lo, lw = w_im - (T)w_lo;                                \
+                const T hh = (T)1 - lh, hw = (T)1 - lw;                                          \
+                const int ok[4] = {h_lo >= 0 && w_lo >= 0, h_lo >= 0 && w_hi <= W - 1,           \
+                                   h_hi <= H - 1 && w_lo >= 0, h_hi <= H - 1 && w_hi <= W - 1};  \
+                const int64_t off[4] = {lvl_off + ((int64_t)h_lo * W + w_lo) * pix_stride,       \
+                                        lvl_off + ((int64_t)h_lo * W + w_hi) * pix_stride,       \
+                                        lvl_off + ((int64_t)h_hi * W + w_lo) * pix_stride,       \
+                                        lvl_off + ((int64_t)h_hi * W + w_hi) * pix_stride};      \
+                const T cw[4] = {hh * hw, hh * lw, lh * hw, lh * lw};       /* :103 */           \
+                const T dh[4] = {-hw, -lw, hw, lw};   /* d(cw)/d(h_im), :111,:118,:125,:132 */   \
+                const T dw[4] = {-hh, hh, -lh, lh};   /* d(cw)/d(w_im), :112,:119,:126,:133 */   \
+                for (int64_t c = 0; c < D; ++c) {                                                \
+                  const T tg = go[c];                                                            \
+                  const T tgv = tg * aw;              /* :104 */                                 \
+                  T val = (T)0, gh = (T)0, gw = (T)0;                                            \
+                  for (int j = 0; j < 4; ++j) {                                                  \
+                    if (!ok[j]) continue;                                                        \
+                    const T v = value[off[j] + c];                                               \
+                    val += cw[j] * v;                                                            \
+                    gh += dh[j] * v;                                                             \
+                    gw += dw[j] * v;                                                             \
+                    grad_value[off[j] + c] += cw[j] * tgv;                  /* :113 */           \
+                  }                                                                              \
+                  g_w += tg * val;                                          /* :138 */           \
+                  g_x += (T)W * gw * tgv;                                   /* :139 */           \
+                  g_y += (T)H * gh * tgv;                                   /* :140 */           \
+                }                                                                                \
+              }                                                                                  \
+              grad_loc[si * 2] = g_x;                                                            \
+              grad_loc[si * 2 + 1] = g_y;                                                        \
+              grad_weight[si] = g_w;                                                             \
+            }                                                                                    \
+          }                                                                                      \
+        }                                                                                        \
+  }
+
+DEFINE_ORACLE_BWD(msda_oracle_backward_f32, float, floorf)
+DEFINE_ORACLE_BWD(msda_oracle_backward_f64, double, floor)

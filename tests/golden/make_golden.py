@@ -29,6 +29,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 REFERENCE_OPS = "/root/reference/codetr/ops.py"
+GRAD_CASES = ("ref_seed3", "edge_borders", "codino_dec_tiny", "odd_dims")
 
 
 def load_reference_function():
@@ -59,7 +60,18 @@ def main() -> None:
             w = torch.from_numpy(arrs["attn_weight"]).to(dt)
             with torch.no_grad():
                 outs[tag] = ref_fn(v, shapes, loc, w).numpy()
+        # gradients: autograd through the reference's own (differentiable) function, fp64, for a seeded
+        # grad_output; the reference's backward kernel is tested against exactly this (tests:367-414)
+        grads = {}
+        if case.name in GRAD_CASES:
+            g = np.random.default_rng(4242).standard_normal(outs["f64"].shape)
+            v = torch.from_numpy(arrs["value"]).double().requires_grad_(True)
+            loc = torch.from_numpy(arrs["sampling_loc"]).double().requires_grad_(True)
+            w = torch.from_numpy(arrs["attn_weight"]).double().requires_grad_(True)
+            ref_fn(v, shapes, loc, w).backward(torch.from_numpy(g))
+            grads = {"grad_out": g, "grad_value": v.grad.numpy(), "grad_loc": loc.grad.numpy(), "grad_weight": w.grad.numpy()}
         payload = {
+            **grads,
             "out_f32": outs["f32"],
             "out_f64": outs["f64"],
             "digest": np.frombuffer(inputs_digest(arrs).encode(), dtype=np.uint8),
