@@ -48,7 +48,7 @@ def parse_args():
     ap.add_argument("--workload", default=None, help="name in codetr_b200.workloads.CONFIGS (default: headline)")
     ap.add_argument("--batch", type=int, default=None, help="images per GPU per step (default: the workload's)")
     ap.add_argument("--dtype", default=None, choices=[None, "float16", "bfloat16", "float32"])
-    ap.add_argument("--loc-mode", default=None, choices=[None, "encoder", "decoder", "uniform"])
+    ap.add_argument("--loc-mode", default=None, choices=[None, "encoder", "decoder", "uniform", "adversarial"])
     ap.add_argument("--flags", type=int, default=None, help="msda_flags bit field (default: library default)")
     ap.add_argument("--workspace", action="store_true", help="give the library a scratch buffer (packed-pyramid path)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -292,8 +292,43 @@ __global__ void __launch_bounds__(kThreads) msda_fwd_generic(const MsdaParams p)
 // ---------------------------------------------------------------------------
 enum MathMode { kExact = 0, kFhfma = 1 };
 
+// Cache policy knobs (compile-time, for the tuning builds): MSDA_VALUE_HINT 0 = plain read-only load,
+// 1 = L1::evict_last (value rows are the reused data); MSDA_STREAM_HINT 0 = plain, 1 = L1::no_allocate for the
+// streamed-once inputs (locations, weights) so they do not displace value rows from L1.
+#ifndef MSDA_VALUE_HINT
+#define MSDA_VALUE_HINT 0
+#endif
+#ifndef MSDA_STREAM_HINT
+#define MSDA_STREAM_HINT 0
+#endif
+
 __device__ __forceinline__ uint4 ldg128(const void *ptr) {
+#if MSDA_VALUE_HINT == 1
+  uint4 r;
+  asm volatile("ld.global.nc.L1::evict_last.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(ptr));
+  return r;
+#else
   return __ldg(static_cast<const uint4 *>(ptr));
+#endif
+}
+
+__device__ __forceinline__ unsigned ld_stream_u32(const void *ptr) {
+#if MSDA_STREAM_HINT == 1
+  unsigned r;
+  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(ptr));
+  return r;
+#else
+  return __ldg(static_cast<const unsigned *>(ptr));
+#endif
+}
+__device__ __forceinline__ unsigned short ld_stream_u16(const void *ptr) {
+#if MSDA_STREAM_HINT == 1
+  unsigned short r;
+  asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(r) : "l"(ptr));
+  return r;
+#else
+  return __ldg(static_cast<const unsigned short *>(ptr));
+#endif
 }
 
 // acc[0..VEC) += cw * row, for one 16-byte piece of a corner row
@@ -470,10 +505,10 @@ __device__ __forceinline__ void make_geo(float x, float y, float aw, int H, int 
 template <typename T>
 __device__ __forceinline__ void load_sample_inputs(const T *lp, const T *wp, int si, float &x, float &y, float &aw) {
   if constexpr (sizeof(T) == 2) {
-    const float2 xy = unpack2<T>(__ldg(reinterpret_cast<const unsigned *>(lp) + si));
+    const float2 xy = unpack2<T>(ld_stream_u32(reinterpret_cast<const unsigned *>(lp) + si));
     x = xy.x;
     y = xy.y;
-    const unsigned short wraw = __ldg(reinterpret_cast<const unsigned short *>(wp) + si);
+    const unsigned short wraw = ld_stream_u16(reinterpret_cast<const unsigned short *>(wp) + si);
     aw = unpack2<T>((unsigned)wraw).x;
   } else {
     const float2 xy = __ldg(reinterpret_cast<const float2 *>(lp) + si);

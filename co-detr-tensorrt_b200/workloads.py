@@ -147,13 +147,17 @@ def make_inputs(
     ``loc_mode``: "encoder" (reference point = the query's own pixel centre, offsets of a few
     pixels along the head's direction, transformer.py:280-305 + module init), "decoder"
     (reference boxes, ``cxcy + off/P * wh/2``), or "uniform" (``rand`` in [0,1), what the
-    reference's tests use -- worst case for locality).  ``out_of_range_frac`` pushes that share of
+    reference's tests use -- worst case for locality), or "adversarial" (the workload's own pattern with
+    5 % of the locations thrown to [-0.5, 1.5]).  ``out_of_range_frac`` pushes that share of
     locations outside [0,1] (boundary parity).  ``pad_frac`` zeroes a right/bottom band of keys, like
     ``masked_fill(key_padding_mask)`` (multi_scale_deformable_attention.py:174-175).
     """
     B = wl.batch if batch is None else int(batch)
     rng = np.random.default_rng(wl.seed if seed is None else seed)
     mode = loc_mode or wl.kind
+    if mode == "adversarial":  # the workload's own pattern with 5 % of the locations pushed outside [0, 1]
+        mode = wl.kind if wl.kind != "uniform" else "uniform"
+        out_of_range_frac = max(out_of_range_frac, 0.05)
     M, D, P, L, S, Q = wl.num_heads, wl.channels, wl.num_points, wl.L, wl.S, wl.Q
     shapes = np.asarray(wl.shapes, dtype=np.int64).reshape(L, 2)
     starts = np.asarray(level_starts(wl.shapes), dtype=np.int64)

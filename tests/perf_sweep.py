@@ -102,6 +102,7 @@ def main():
         del buf
 
     workloads = [("swinl_enc_1152x768", 1, "float16", None), ("swinl_enc_1152x768", 1, "float16", "uniform"),
+                 ("swinl_enc_1152x768", 1, "float16", "adversarial"),
                  ("swinl_enc_1152x768", 4, "float16", None), ("swinl_enc_1152x768", 1, "bfloat16", None),
                  ("swinl_enc_1152x768", 1, "float32", None),
                  ("r50_enc_608", 1, "float16", None), ("swinl_dec_1152x768", 1, "float16", None),

@@ -538,3 +538,15 @@ def test_packed_path_full_size_and_torch_op(cuda_device):
                              out2.data_ptr(), s.cuda_stream, workspace_ptr=ws.data_ptr(), workspace_bytes=need) == 0
     s.synchronize()
     assert torch.equal(out2, direct)
+
+
+@pytest.mark.parametrize("name", ["swinl_enc_1152x768", "swinl_dec_1152x768"])
+def test_full_size_adversarial_locations(name, cuda_device):
+    """~5 % of the locations outside [0, 1] at full size (boundary parity)."""
+    wl = W.CONFIGS[name]
+    inp = W.make_inputs(wl, batch=1, loc_mode="adversarial")
+    assert ((inp.sampling_loc < 0) | (inp.sampling_loc > 1)).mean() > 0.03
+    arrs = {k: getattr(inp, k) for k in ARRAY_KEYS}
+    for dt, gate, metric in (("f32", FP32_REL_L2, rel_l2), ("f16", HALF_MAX_REL, max_rel)):
+        out, d = run_op(arrs, TORCH_DT[dt], cuda_device)
+        assert metric(out.float().cpu().numpy(), ref32_of(d)) <= gate
