@@ -535,6 +535,55 @@ __device__ __forceinline__ void load_sample_inputs_smem(const unsigned char *lp,
   }
 }
 
+// Undecoded location + weight of one sample: loaded early (next level / next pass), converted at use, so
+// the conversion never becomes the point where the warp waits for the load.
+struct RawSample {
+  unsigned a, b, w;  // 16-bit types: a = packed (x, y), w = weight bits; fp32: a = x, b = y, w = weight
+};
+template <typename T>
+__device__ __forceinline__ RawSample load_raw(const T *lp, const T *wp, int si) {
+  RawSample r;
+  if constexpr (sizeof(T) == 2) {
+    r.a = ld_stream_u32(reinterpret_cast<const unsigned *>(lp) + si);
+    r.b = 0u;
+    r.w = (unsigned)ld_stream_u16(reinterpret_cast<const unsigned short *>(wp) + si);
+  } else {
+    const float2 xy = __ldg(reinterpret_cast<const float2 *>(lp) + si);
+    r.a = __float_as_uint(xy.x);
+    r.b = __float_as_uint(xy.y);
+    r.w = __float_as_uint(__ldg(reinterpret_cast<const float *>(wp) + si));
+  }
+  return r;
+}
+template <typename T>
+__device__ __forceinline__ RawSample load_raw_smem(const unsigned char *lp, const unsigned char *wp, int si) {
+  RawSample r;
+  if constexpr (sizeof(T) == 2) {
+    r.a = reinterpret_cast<const unsigned *>(lp)[si];
+    r.b = 0u;
+    r.w = (unsigned)reinterpret_cast<const unsigned short *>(wp)[si];
+  } else {
+    const float2 xy = reinterpret_cast<const float2 *>(lp)[si];
+    r.a = __float_as_uint(xy.x);
+    r.b = __float_as_uint(xy.y);
+    r.w = __float_as_uint(reinterpret_cast<const float *>(wp)[si]);
+  }
+  return r;
+}
+template <typename T>
+__device__ __forceinline__ void decode_raw(const RawSample &r, float &x, float &y, float &aw) {
+  if constexpr (sizeof(T) == 2) {
+    const float2 xy = unpack2<T>(r.a);
+    x = xy.x;
+    y = xy.y;
+    aw = unpack2<T>(r.w).x;
+  } else {
+    x = __uint_as_float(r.a);
+    y = __uint_as_float(r.b);
+    aw = __uint_as_float(r.w);
+  }
+}
+
 // two fp32 weights -> packed 16-bit pair in the element type (low half = first)
 template <typename T>
 __device__ __forceinline__ unsigned pack_weights(float a, float b);
@@ -801,31 +850,48 @@ __global__ void __launch_bounds__(kThreads, (SPLIT > 1 && P_T == 4) ? MSDA_MINB_
     if (threadIdx.x == 0 && (int)blockIdx.x < total) stage_issue(blockIdx.x, 0);
   }
 
+  // (tile, pass) unit -> this lane group's query (or -1 for a padding slot) and head
+  auto decode_unit = [&](int w, int &q, int &m) {
+    int pass;
+    const int t = fast_div(w, p.passes, p.inv_passes, pass);
+    int tq;
+    if (p.qpp) {
+      tq = pass * p.qpp + tql;
+      m = m_fixed;
+      q = tile_query(p, ts, t, tq);
+    } else {
+      const int s = pass * PAIRS_PER_PASS + ls;
+      if (p.head_major) {
+        // slots ordered [query block of PPW][head][query in block]: a warp holds one head of PPW
+        // neighbouring queries
+        const int g = s & (PPW - 1);
+        const int qb = fast_div(s / PPW, M, p.inv_M, m);
+        tq = qb * PPW + g;
+      } else {
+        tq = fast_div(s, M, p.inv_M, m);
+      }
+      q = (s < slots) ? tile_query(p, ts, t, tq) : -1;
+    }
+  };
+  auto pair_index = [&](int q, int m) -> int64_t { return q >= 0 ? ((int64_t)b * p.Q + q) * M + m : 0; };
+
+  // The CTA is persistent (it strides over the units), so the first sample of the NEXT unit is loaded
+  // while the current one is computed: `carry` holds its undecoded location / weight.
+  constexpr bool kCarry = (P_T == 4 && SPLIT == 1 && G >= 4 && !STAGE);
+  int q = -1, m = 0;
+  RawSample carry = {0u, 0u, 0u};
+  if ((int)blockIdx.x < total) {
+    decode_unit(blockIdx.x, q, m);
+    if constexpr (kCarry) {
+      const int64_t pr = pair_index(q, m);
+      carry = load_raw<T>(loc + pr * LP * 2, wgt + pr * LP, sub & 3);
+    }
+  }
+
   int it = 0;
   for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
-    int q, m;
-    {
-      int pass;
-      const int t = fast_div(w, p.passes, p.inv_passes, pass);
-      int tq;
-      if (p.qpp) {
-        tq = pass * p.qpp + tql;
-        m = m_fixed;
-        q = tile_query(p, ts, t, tq);
-      } else {
-        const int s = pass * PAIRS_PER_PASS + ls;
-        if (p.head_major) {
-          // slots ordered [query block of PPW][head][query in block]: a warp holds one head of PPW
-          // neighbouring queries
-          const int g = s & (PPW - 1);
-          const int qb = fast_div(s / PPW, M, p.inv_M, m);
-          tq = qb * PPW + g;
-        } else {
-          tq = fast_div(s, M, p.inv_M, m);
-        }
-        q = (s < slots) ? tile_query(p, ts, t, tq) : -1;
-      }
-    }
+    int q_next = -1, m_next = m;
+    if (w + (int)gridDim.x < total) decode_unit(w + gridDim.x, q_next, m_next);
     const unsigned char *slp = nullptr, *swp = nullptr;
     if constexpr (STAGE) {
       const int buf = it & 1;
@@ -859,9 +925,9 @@ __global__ void __launch_bounds__(kThreads, (SPLIT > 1 && P_T == 4) ? MSDA_MINB_
         // zero, and a zero weight predicates both the load and the FMAs of that corner off.
         constexpr unsigned group_mask = 0xffffffffu;
         const int ks = sub & 3;
-        float nx, ny, naw;
-        if constexpr (STAGE) load_sample_inputs_smem<T>(slp, swp, ks, nx, ny, naw);
-        else load_sample_inputs<T>(lp, wp, ks, nx, ny, naw);
+        RawSample raw;
+        if constexpr (STAGE) raw = load_raw_smem<T>(slp, swp, ks);
+        else raw = carry;  // loaded during the previous unit (or before the loop)
         // fused mode: softmax statistics of the pair's L*4 logits.  Lane ks holds the logits of point ks
         // of every level; maximum and sum are completed across the four point-lanes with two butterflies.
         float sm_max = 0.f, sm_inv = 1.f;
@@ -881,15 +947,25 @@ __global__ void __launch_bounds__(kThreads, (SPLIT > 1 && P_T == 4) ? MSDA_MINB_
         }
         for (int l = 0; l < p.L; ++l) {
           const int H = ts.lv[l].H, W = ts.lv[l].W;
-          float x = nx, y = ny, aw = live ? naw : 0.f;
+          float x, y, aw;
+          decode_raw<T>(raw, x, y, aw);
           if constexpr (FUSED) {
-            // nx, ny are the raw offsets, naw the logit
-            fused_location<T, float>(rfp + l * p.ref_dim, p.ref_dim, nx, ny, H, W, 4, x, y);
-            aw = live ? round_like<T, float>(fused_exp<T>(naw - sm_max) * sm_inv) : 0.f;
+            // x, y are the raw offsets, aw the logit
+            const float ox = x, oy = y;
+            fused_location<T, float>(rfp + l * p.ref_dim, p.ref_dim, ox, oy, H, W, 4, x, y);
+            aw = round_like<T, float>(fused_exp<T>(aw - sm_max) * sm_inv);
           }
-          if (l + 1 < p.L) {  // prefetch next level
-            if constexpr (STAGE) load_sample_inputs_smem<T>(slp, swp, (l + 1) * 4 + ks, nx, ny, naw);
-            else load_sample_inputs<T>(lp, wp, (l + 1) * 4 + ks, nx, ny, naw);
+          aw = live ? aw : 0.f;
+          // prefetch: next level of this unit, or the first level of the next unit
+          if constexpr (STAGE) {
+            if (l + 1 < p.L) raw = load_raw_smem<T>(slp, swp, (l + 1) * 4 + ks);
+          } else {
+            if (l + 1 < p.L) {
+              raw = load_raw<T>(lp, wp, (l + 1) * 4 + ks);
+            } else {
+              const int64_t pn = pair_index(q_next, m_next);
+              raw = load_raw<T>(loc + pn * LP * 2, wgt + pn * LP, ks);
+            }
           }
           int i00;
           float cw[4];
@@ -940,6 +1016,7 @@ __global__ void __launch_bounds__(kThreads, (SPLIT > 1 && P_T == 4) ? MSDA_MINB_
             }
           }
         }
+        if constexpr (kCarry) carry = raw;
       } else if constexpr (P_T == 4) {
         // ---- split-points path (small Q, e.g. the decoder's 900 queries): the four points of a level are
         // dealt to SPLIT lane groups, and the row loads of LB levels are all issued before the first FMA,
@@ -1032,6 +1109,8 @@ __global__ void __launch_bounds__(kThreads, (SPLIT > 1 && P_T == 4) ? MSDA_MINB_
       }
       if (live && split == 0) store_row<T, VEC>(out + pair * D + sub * VEC, acc);
     }
+    q = q_next;
+    m = m_next;
   }
 }
 
@@ -1744,8 +1823,13 @@ int forward_impl(MsdaParams p, int dtype, unsigned flags, void *workspace, size_
   if ((int64_t)p.Q * passes >= ((int64_t)1 << 22) || tile_q * p.M >= ((int64_t)1 << 22) || p.B > 65535) {
     return run_generic(p, dtype, stream);
   }
+  // Persistent grid: exactly the resident CTA count (4 per SM) for launches of up to ~32 passes per SM,
+  // twice that for larger ones; every CTA strides over the passes, so the per-CTA set-up (level table,
+  // barrier) is paid once.  Measured vs one CTA per pass: 51.2 vs 54.7 us at the headline shape, 91.6 vs
+  // 100.7 us in fp32 (profiles/r01_sweep_ctas.log).
   int64_t grid = tiles_est * passes;
-  const int64_t cap = ((int64_t)sms * env_int("MSDA_B200_CTAS_PER_SM", 32) + p.B - 1) / p.B;
+  const int64_t per_sm = (grid * p.B + sms - 1) / sms;
+  const int64_t cap = ((int64_t)sms * env_int("MSDA_B200_CTAS_PER_SM", per_sm <= 32 ? 4 : 8) + p.B - 1) / p.B;
   if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;
   plan.grid = (unsigned)grid;

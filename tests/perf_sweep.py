@@ -111,6 +111,10 @@ def main():
                  ("ref_test_mid_fp32", 1, "float32", None)]
     if args.quick:
         workloads = workloads[:2]
+    if args.only == "ctas":
+        workloads = [("swinl_enc_1152x768", 1, "float16", None), ("swinl_enc_1152x768", 4, "float16", None),
+                     ("swinl_enc_1152x768", 1, "float32", None), ("swinl_enc_1920x1280", 2, "float16", None),
+                     ("r50_enc_608", 1, "float16", None), ("swinl_dec_1152x768", 8, "float16", None)]
     if args.only == "decoder":
         workloads = [("swinl_dec_1152x768", 1, "float16", None), ("swinl_dec_1900q", 1, "float16", None),
                      ("swinl_dec_1152x768", 8, "float16", None), ("ref_test_mid_fp32", 1, "float32", None),
@@ -133,6 +137,7 @@ def main():
     ]
     tile_cfgs = [{"name": f"tile{w}x{h}+fhfma", "flags": cb.FLAG_MATH_FHFMA, "MSDA_B200_TILE_W": w, "MSDA_B200_TILE_H": h}
                  for (w, h) in ((8, 1), (8, 2), (8, 8), (16, 2), (16, 4), (4, 4), (32, 2), (32, 8))]
+    ctas_cfgs = [{"name": f"ctas_per_sm{c}", "flags": 0, "MSDA_B200_CTAS_PER_SM": c} for c in (4, 8, 12, 16)]
     split_cfgs = [{"name": f"split{s}", "flags": 0, "MSDA_B200_SPLIT": s} for s in (1, 2, 4)]
     split_cfgs += [{"name": f"split{s}+fhfma", "flags": cb.FLAG_MATH_FHFMA, "MSDA_B200_SPLIT": s} for s in (1, 4)]
 
@@ -150,6 +155,9 @@ def main():
             cfgs += split_cfgs
         if dtn == "float32":
             cfgs = [c for c in cfgs if "fhfma" not in c["name"]]
+        if args.only == "ctas":
+            cfgs = [{"name": "default", "flags": 0}] + ctas_cfgs
+            have_ref = False
         if args.only == "decoder":
             cfgs = [c for c in split_cfgs if "fhfma" not in c["name"]] + [{"name": "default", "flags": 0}]
             have_ref = False
