@@ -83,54 +83,78 @@ def committed_traffic(workload: str, dtype: str, batch: int):
         return None
 
 
-class ClockSampler(threading.Thread):
-    """Samples SM clock / throttle reasons of one GPU through NVML while the timed region runs."""
+class ClockSampler:
+    """Samples SM clock / throttle reasons of one GPU DURING the timed region with the profiling recipe's
+    `nvidia-smi --query-gpu=... -lms` line, run as a separate process (a Python thread would starve behind
+    the launch loop's GIL); NVML in-process as a fallback when nvidia-smi is missing."""
 
-    def __init__(self, index: int, period_s: float = 0.004):
-        super().__init__(daemon=True)
-        self.index, self.period = index, period_s
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+
+    def __init__(self, index: int, period_ms: int = 20):
+        import shutil
+        import subprocess
+        import tempfile
+
+        self.index, self.proc, self.path = index, None, None
         self.samples, self.reasons, self.max_mhz = [], set(), None
-        self._stop = threading.Event()
-        self.ok = False
-        try:
+        exe = shutil.which("nvidia-smi")
+        if exe:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.out = open(self.path, "w")
+            self.proc = subprocess.Popen([exe, "-i", str(index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", str(period_ms)], stdout=self.out, stderr=subprocess.DEVNULL)
+        self.t_start = None
+
+    def start(self):
+        # drop whatever was sampled while the GPU was idle before the timed region
+        self.t_start = time.time()
+        if self.proc is not None:
+            self.out.flush()
+            self.skip = os.path.getsize(self.path)
+
+    def sample_once(self):
+        try:  # NVML fallback / extra sample while the queue drains
             import pynvml
 
             pynvml.nvmlInit()
-            self.nv = pynvml
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
-            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
-            self.ok = True
-        except Exception:
-            self.ok = False
-
-    def sample_once(self):
-        if not self.ok:
-            return
-        nv = self.nv
-        try:
-            self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
-            try:
-                mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
-            except Exception:
-                mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
-            names = {
-                0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
-                0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost",
-                0x100: "display_clock_setting",
-            }
-            for bit, name in names.items():
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.samples.append(int(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            mask = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+            for bit, name in ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap")):
                 if mask & bit:
                     self.reasons.add(name)
         except Exception:
             pass
 
-    def run(self):
-        while not self._stop.is_set():
-            self.sample_once()
-            time.sleep(self.period)
-
     def stop(self):
-        self._stop.set()
+        if self.proc is None:
+            return
+        time.sleep(0.03)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.out.close()
+        try:
+            with open(self.path) as f:
+                f.seek(getattr(self, "skip", 0))
+                for line in f:
+                    parts = [x.strip() for x in line.split(",")]
+                    if len(parts) < 6 or not parts[0].isdigit():
+                        continue
+                    self.samples.append(int(parts[0]))
+                    self.max_mhz = int(parts[1]) if parts[1].isdigit() else self.max_mhz
+                    for name, val in zip(self.NAMES, parts[2:6]):
+                        if val.lower().startswith("active"):
+                            self.reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
 
     def summary(self):
         if not self.samples:

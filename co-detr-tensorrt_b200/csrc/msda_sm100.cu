@@ -1829,7 +1829,7 @@ int forward_impl(MsdaParams p, int dtype, unsigned flags, void *workspace, size_
   // 100.7 us in fp32 (profiles/r01_sweep_ctas.log).
   int64_t grid = tiles_est * passes;
   const int64_t per_sm = (grid * p.B + sms - 1) / sms;
-  const int64_t cap = ((int64_t)sms * env_int("MSDA_B200_CTAS_PER_SM", per_sm <= 32 ? 4 : 8) + p.B - 1) / p.B;
+  const int64_t cap = ((int64_t)sms * env_int("MSDA_B200_CTAS_PER_SM", per_sm <= 32 ? MSDA_MINB : 2 * MSDA_MINB) + p.B - 1) / p.B;
   if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;
   plan.grid = (unsigned)grid;
