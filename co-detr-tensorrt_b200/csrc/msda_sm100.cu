@@ -49,6 +49,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 
 #include "msda_b200.h"
 
@@ -1115,6 +1116,93 @@ __global__ void __launch_bounds__(kThreads, (SPLIT > 1 && P_T == 4) ? MSDA_MINB_
 }
 
 // ---------------------------------------------------------------------------
+// Small-problem kernel (decoder cross-attention: 900 queries = 7,200 pairs).  The general kernel spends a
+// third of its instructions on per-CTA set-up and tile decode, which a launch this small cannot amortise
+// (ncu: 3.46 M instructions for 7,200 pairs, issue-bound at 10 us even with warm L2).  Here: no shared
+// memory, no barrier, no tiles -- lane l of every warp loads level l's (H, W, start) and hands it out by
+// shuffle; 4 lane groups of G lanes share a pair (one point of each level per group) and are reduced
+// with butterflies; 128-thread CTAs so that 7,200 pairs spread over all 148 SMs.
+// ---------------------------------------------------------------------------
+constexpr int kSmallThreads = 128;
+
+template <typename T, int D, int MATH>
+__global__ void __launch_bounds__(kSmallThreads, 8) msda_fwd_small(const MsdaParams p) {
+  constexpr int E = (int)sizeof(T), VEC = 16 / E, G = D / VEC, GS = G * 4;
+  static_assert(GS <= 32, "rows wider than 8 lanes do not fit the 4-way point split");
+  const char *__restrict__ value = static_cast<const char *>(p.value);
+  const T *__restrict__ loc = static_cast<const T *>(p.loc);
+  const T *__restrict__ wgt = static_cast<const T *>(p.weight);
+  T *__restrict__ out = static_cast<T *>(p.out);
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % G, split = (lane / G) & 3;
+  const int M = p.M, LP = p.L * 4;
+  const unsigned pix_bytes = (unsigned)(M * D * E);
+
+  // level table: lane l holds level l (L <= 32 guaranteed by the host)
+  int lvH = 0, lvW = 0, lvS = 0;
+  if (lane < p.L) {
+    lvH = (int)__ldg(p.shapes + 2 * lane);
+    lvW = (int)__ldg(p.shapes + 2 * lane + 1);
+    lvS = (int)__ldg(p.starts + lane);
+  }
+
+  const int64_t pairs = (int64_t)p.B * p.Q * M;
+  const int64_t pr = ((int64_t)blockIdx.x * kSmallThreads + threadIdx.x) / GS;
+  const bool live = pr < pairs;
+  const int64_t pair = live ? pr : 0;
+  const int m = (int)(pair % M);
+  const int64_t b = pair / M / p.Q;
+  const T *lp = loc + pair * LP * 2;
+  const T *wp = wgt + pair * LP;
+  const char *vm = value + ((size_t)b * p.S * M + m) * (size_t)(D * E) + (size_t)sub * 16;
+
+  // all of this lane's samples (point `split` of every level) are requested before anything is decoded
+  constexpr int kMaxL = 8;
+  RawSample raw[kMaxL];
+#pragma unroll
+  for (int l = 0; l < kMaxL; ++l)
+    if (l < p.L) raw[l] = load_raw<T>(lp, wp, l * 4 + split);
+
+  float acc[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+
+#pragma unroll
+  for (int l = 0; l < kMaxL; ++l) {
+    if (l < p.L) {  // uniform across the grid
+      const int H = __shfl_sync(0xffffffffu, lvH, l), W = __shfl_sync(0xffffffffu, lvW, l);
+      const int start = __shfl_sync(0xffffffffu, lvS, l);
+      float x, y, aw;
+      decode_raw<T>(raw[l], x, y, aw);
+      aw = live ? aw : 0.f;
+      int i00;
+      float cw[4];
+      make_geo(x, y, aw, H, W, i00, cw);
+      i00 += start;
+      uint4 rows[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int idx = i00 + (j & 1) + ((j & 2) ? W : 0);
+        if (cw[j] != 0.f) rows[j] = ldg128(vm + (size_t)(unsigned)idx * pix_bytes);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (cw[j] != 0.f) {
+          if constexpr (MATH == kFhfma) RowFma<T, kFhfma>::run(acc, rows[j], 0.f, weight_to_16<T>(cw[j]));
+          else RowFma<T, kExact>::run(acc, rows[j], cw[j], 0u);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int off = G; off < GS; off <<= 1) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], off);
+  }
+  if (live && split == 0) store_row<T, VEC>(out + pair * D + sub * VEC, acc);
+}
+
+// ---------------------------------------------------------------------------
 // Packed path (16-bit types, D = 32, P = 4): pixel-pair packed pyramid + 256-bit loads.
 //
 // In the channels-last value tensor a (pixel, head) row is 64 B, half an L1 line, so each of the four
@@ -1747,7 +1835,7 @@ int forward_impl(MsdaParams p, int dtype, unsigned flags, void *workspace, size_
   // SMs the un-split kernel wins (measured: R50 encoder 608x608 28 us un-split vs 51 us split).
   const int64_t ctas_unsplit = (pairs * G + kThreads - 1) / kThreads;
   plan.split = 1;
-  if (ctas_unsplit < sms && p.P == 4 && !fused) plan.split = (G * 4 <= 32) ? 4 : ((G * 2 <= 32) ? 2 : 1);
+  if (ctas_unsplit < env_int("MSDA_B200_SPLIT_MAX_CTAS", sms) && p.P == 4 && !fused) plan.split = (G * 4 <= 32) ? 4 : ((G * 2 <= 32) ? 2 : 1);
   if (!fused) plan.split = env_int("MSDA_B200_SPLIT", plan.split);
   if (!((plan.split == 4 && G * 4 <= 32) || (plan.split == 2 && G * 2 <= 32 && p.P == 4))) plan.split = 1;
 
@@ -1834,6 +1922,38 @@ int forward_impl(MsdaParams p, int dtype, unsigned flags, void *workspace, size_
   if (grid < 1) grid = 1;
   plan.grid = (unsigned)grid;
   plan.grid_y = (unsigned)p.B;
+
+  // ---- small-problem kernel (decoder): 4-way point split, no tiles, no barrier ----
+  if (plan.split == 4 && !fused && p.P == 4 && p.L <= 8 && env_int("MSDA_B200_SMALL", 1)) {
+    const int64_t lanes = pairs * G * 4;
+    const unsigned sgrid = (unsigned)((lanes + kSmallThreads - 1) / kSmallThreads);
+    int rc3 = MSDA_ERR_UNSUPPORTED;
+    auto launch_small = [&](auto tag_t, auto tag_d) {
+      using TT = decltype(tag_t);
+      constexpr int DD = decltype(tag_d)::value;
+      if constexpr (DD * (int)sizeof(TT) / 16 * 4 <= 32) {
+        if (sizeof(TT) == 2 && plan.math == kFhfma) {
+          if constexpr (sizeof(TT) == 2) msda_fwd_small<TT, DD, kFhfma><<<sgrid, kSmallThreads, 0, stream>>>(p);
+        } else {
+          msda_fwd_small<TT, DD, kExact><<<sgrid, kSmallThreads, 0, stream>>>(p);
+        }
+        g_launch_count.fetch_add(1, std::memory_order_relaxed);
+        rc3 = (int)cudaGetLastError();
+      }
+    };
+    if (dtype == MSDA_F16 && p.D == 32) launch_small(__half{}, std::integral_constant<int, 32>{});
+    else if (dtype == MSDA_F16 && p.D == 64) launch_small(__half{}, std::integral_constant<int, 64>{});
+    else if (dtype == MSDA_BF16 && p.D == 32) launch_small(__nv_bfloat16{}, std::integral_constant<int, 32>{});
+    else if (dtype == MSDA_BF16 && p.D == 64) launch_small(__nv_bfloat16{}, std::integral_constant<int, 64>{});
+    else if (dtype == MSDA_F32 && p.D == 32) launch_small(float{}, std::integral_constant<int, 32>{});
+    else if (dtype == MSDA_F32 && p.D == 16) launch_small(float{}, std::integral_constant<int, 16>{});
+    if (rc3 != MSDA_ERR_UNSUPPORTED) {
+      if (rc3 == 0)
+        snprintf(g_last_variant, sizeof(g_last_variant), "small<%s,D%d,P4,split4>/%s", dtype_name(dtype), p.D,
+                 plan.math == kFhfma ? "fhfma" : "exact");
+      return rc3;
+    }
+  }
 
   // ---- packed path: pixel-pair packed pyramid in the caller's workspace + 256-bit loads ----
   const size_t packed_need = packed_workspace_bytes(p.B, p.S, p.M, p.D, p.Q, p.L, p.P, dtype);

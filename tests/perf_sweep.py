@@ -59,7 +59,8 @@ def time_calls(fns, iters, warmup=20):
 
 
 def set_env(cfg):
-    for k in ("MSDA_B200_TILE_W", "MSDA_B200_TILE_H", "MSDA_B200_HEAD_MAJOR", "MSDA_B200_SPLIT", "MSDA_B200_CTAS_PER_SM"):
+    for k in ("MSDA_B200_TILE_W", "MSDA_B200_TILE_H", "MSDA_B200_HEAD_MAJOR", "MSDA_B200_SPLIT", "MSDA_B200_CTAS_PER_SM",
+              "MSDA_B200_SMALL", "MSDA_B200_SPLIT_MAX_CTAS"):
         os.environ.pop(k, None)
     for k, v in cfg.items():
         if k.startswith("MSDA_"):
@@ -159,7 +160,11 @@ def main():
             cfgs = [{"name": "default", "flags": 0}] + ctas_cfgs
             have_ref = False
         if args.only == "decoder":
-            cfgs = [c for c in split_cfgs if "fhfma" not in c["name"]] + [{"name": "default", "flags": 0}]
+            cfgs = [{"name": "default", "flags": 0}, {"name": "no-small-kernel", "flags": 0, "MSDA_B200_SMALL": 0},
+                    {"name": "small<=300ctas", "flags": 0, "MSDA_B200_SPLIT_MAX_CTAS": 300},
+                    {"name": "small<=600ctas", "flags": 0, "MSDA_B200_SPLIT_MAX_CTAS": 600},
+                    {"name": "small<=1200ctas", "flags": 0, "MSDA_B200_SPLIT_MAX_CTAS": 1200},
+                    {"name": "split1", "flags": 0, "MSDA_B200_SPLIT": 1}]
             have_ref = False
         if args.only == "headline":
             cfgs = [c for c in cfgs if c["name"] in ("default", "exact-placeholder", "tile8x8+fhfma", "tile16x4+fhfma",

@@ -385,7 +385,7 @@ def test_full_size_configs_against_oracle(name, dt, cuda_device):
     before = cb.launch_count()
     out, d = run_op(arrs, TORCH_DT[dt], cuda_device)
     assert cb.launch_count() == before + 1          # one kernel per call, whatever the batch
-    assert cb.last_variant().startswith("vec<")     # the Co-DINO shapes take the vector kernel
+    assert cb.last_variant().startswith(("vec<", "small<"))     # the Co-DINO shapes take the vector kernels
     ref = ref32_of(d)
     if dt == "f32":
         assert rel_l2(out.cpu().numpy(), ref) <= FP32_REL_L2
@@ -550,3 +550,23 @@ def test_full_size_adversarial_locations(name, cuda_device):
     for dt, gate, metric in (("f32", FP32_REL_L2, rel_l2), ("f16", HALF_MAX_REL, max_rel)):
         out, d = run_op(arrs, TORCH_DT[dt], cuda_device)
         assert metric(out.float().cpu().numpy(), ref32_of(d)) <= gate
+
+
+@pytest.mark.parametrize("dt", ["f32", "f16", "bf16"])
+def test_small_problem_kernel_matches_general_kernel(dt, cuda_device, monkeypatch):
+    """The decoder-sized launch takes msda_fwd_small (4-way point split, no tiles); forcing the general
+    kernel on the same tensors must give the same values up to the order of the split reduction."""
+    arrs = _full_inputs("swinl_dec_1152x768", 1)
+    if dt == "f32":  # fp32 rows are 8 lanes wide: 225 un-split CTAs already cover the SMs, so force the split
+        monkeypatch.setenv("MSDA_B200_SPLIT_MAX_CTAS", "100000")
+    out, d = run_op(arrs, TORCH_DT[dt], cuda_device)
+    assert cb.last_variant().startswith("small<")
+    monkeypatch.setenv("MSDA_B200_SMALL", "0")
+    monkeypatch.setenv("MSDA_B200_SPLIT", "1")
+    gen = cb.multi_scale_deformable_attention(*(d[k] for k in ARRAY_KEYS))
+    assert cb.last_variant().startswith("vec<")
+    ref = ref32_of(d)
+    gate = {"f32": 1e-5, "f16": HALF_MAX_REL, "bf16": BF16_MAX_REL}[dt]
+    metric = rel_l2 if dt == "f32" else max_rel
+    assert metric(out.float().cpu().numpy(), ref) <= gate
+    assert metric(gen.float().cpu().numpy(), ref) <= gate
