@@ -128,6 +128,7 @@ struct MsdaParams {
   int stage_loc_row, stage_w_row;  // padded shared-memory row pitch (bytes) of one query's locations / weights
   int want_tiled;       // 1: use 2-D tiles when sum(H*W) == Q
   int head_major;       // 1: a warp holds one head of 32/G neighbouring queries
+  int chunked;          // 1: each CTA owns a contiguous run of (tile, pass) units instead of a strided set
 };
 
 struct LevelGeom {
@@ -847,9 +848,6 @@ __global__ void __launch_bounds__(kThreads, (SPLIT > 1 && P_T == 4) ? MSDA_MINB_
       tma_bulk_g2s(dw + i * p.stage_w_row, gw + (size_t)i * w_bytes, w_bytes, &stage_bar[buf]);
     }
   };
-  if constexpr (STAGE) {
-    if (threadIdx.x == 0 && (int)blockIdx.x < total) stage_issue(blockIdx.x, 0);
-  }
 
   // (tile, pass) unit -> this lane group's query (or -1 for a padding slot) and head
   auto decode_unit = [&](int w, int &q, int &m) {
@@ -881,23 +879,40 @@ __global__ void __launch_bounds__(kThreads, (SPLIT > 1 && P_T == 4) ? MSDA_MINB_
   constexpr bool kCarry = (P_T == 4 && SPLIT == 1 && G >= 4 && !STAGE);
   int q = -1, m = 0;
   RawSample carry = {0u, 0u, 0u};
-  if ((int)blockIdx.x < total) {
-    decode_unit(blockIdx.x, q, m);
+  // Unit assignment: `chunked` gives every CTA one contiguous run of units -- it then sweeps whole tiles
+  // row by row, so the corner rows shared by vertically adjacent queries are still in this SM's L1 --
+  // otherwise units are dealt round-robin (stride = grid size).
+  int w_begin, w_end, w_step;
+  if (p.chunked) {
+    const int per = (total + (int)gridDim.x - 1) / (int)gridDim.x;
+    w_begin = (int)blockIdx.x * per;
+    w_end = min(total, w_begin + per);
+    w_step = 1;
+  } else {
+    w_begin = blockIdx.x;
+    w_end = total;
+    w_step = gridDim.x;
+  }
+  if (w_begin < w_end) {
+    decode_unit(w_begin, q, m);
     if constexpr (kCarry) {
       const int64_t pr = pair_index(q, m);
       carry = load_raw<T>(loc + pr * LP * 2, wgt + pr * LP, sub & 3);
     }
+    if constexpr (STAGE) {
+      if (threadIdx.x == 0) stage_issue(w_begin, 0);
+    }
   }
 
   int it = 0;
-  for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+  for (int w = w_begin; w < w_end; w += w_step, ++it) {
     int q_next = -1, m_next = m;
-    if (w + (int)gridDim.x < total) decode_unit(w + gridDim.x, q_next, m_next);
+    if (w + w_step < w_end) decode_unit(w + w_step, q_next, m_next);
     const unsigned char *slp = nullptr, *swp = nullptr;
     if constexpr (STAGE) {
       const int buf = it & 1;
       __syncthreads();  // every thread has finished reading buffer buf^1 (previous pass)
-      if (threadIdx.x == 0 && w + (int)gridDim.x < total) stage_issue(w + gridDim.x, buf ^ 1);
+      if (threadIdx.x == 0 && w + w_step < w_end) stage_issue(w + w_step, buf ^ 1);
       mbar_wait(&stage_bar[buf], (unsigned)((it >> 1) & 1));
       slp = stage_mem + buf * stage_buf_bytes + tql * p.stage_loc_row + m * (LP * 2 * E);
       swp = stage_mem + buf * stage_buf_bytes + p.qpp * p.stage_loc_row + tql * p.stage_w_row + m * (LP * E);
@@ -1858,6 +1873,7 @@ int forward_impl(MsdaParams p, int dtype, unsigned flags, void *workspace, size_
   // loads are contiguous) measured 4-5 % faster than head-major (a warp holds one head of neighbouring
   // queries) once the kernel stopped being wavefront-bound; MSDA_FLAG_HEAD_MAJOR / the env knob switch
   p.head_major = env_int("MSDA_B200_HEAD_MAJOR", (flags & MSDA_FLAG_HEAD_MAJOR) ? 1 : 0);
+  p.chunked = env_int("MSDA_B200_CHUNKED", 0);  // measured: contiguous runs are 3 % slower (imbalance) than round-robin
   int tile_w = env_int("MSDA_B200_TILE_W", 8);
   int tile_h = env_int("MSDA_B200_TILE_H", p.want_tiled ? 4 : 1);
   if (!p.want_tiled) {

@@ -60,7 +60,7 @@ def time_calls(fns, iters, warmup=20):
 
 def set_env(cfg):
     for k in ("MSDA_B200_TILE_W", "MSDA_B200_TILE_H", "MSDA_B200_HEAD_MAJOR", "MSDA_B200_SPLIT", "MSDA_B200_CTAS_PER_SM",
-              "MSDA_B200_SMALL", "MSDA_B200_SPLIT_MAX_CTAS"):
+              "MSDA_B200_SMALL", "MSDA_B200_SPLIT_MAX_CTAS", "MSDA_B200_CHUNKED"):
         os.environ.pop(k, None)
     for k, v in cfg.items():
         if k.startswith("MSDA_"):
@@ -112,6 +112,10 @@ def main():
                  ("ref_test_mid_fp32", 1, "float32", None)]
     if args.quick:
         workloads = workloads[:2]
+    if args.only == "chunk":
+        workloads = [("swinl_enc_1152x768", 1, "float16", None), ("swinl_enc_1152x768", 4, "float16", None),
+                     ("swinl_enc_1152x768", 1, "float32", None), ("swinl_enc_1920x1280", 2, "float16", None),
+                     ("r50_enc_608", 1, "float16", None)]
     if args.only == "ctas":
         workloads = [("swinl_enc_1152x768", 1, "float16", None), ("swinl_enc_1152x768", 4, "float16", None),
                      ("swinl_enc_1152x768", 1, "float32", None), ("swinl_enc_1920x1280", 2, "float16", None),
@@ -156,6 +160,12 @@ def main():
             cfgs += split_cfgs
         if dtn == "float32":
             cfgs = [c for c in cfgs if "fhfma" not in c["name"]]
+        if args.only == "chunk":
+            cfgs = [{"name": "default", "flags": 0}, {"name": "strided", "flags": 0, "MSDA_B200_CHUNKED": 0}]
+            cfgs += [{"name": f"chunked tile{w}x{h}", "flags": 0, "MSDA_B200_TILE_W": w, "MSDA_B200_TILE_H": h}
+                     for (w, h) in ((8, 1), (8, 2), (8, 8), (8, 16), (16, 4), (16, 8), (32, 8))]
+            cfgs += [{"name": "chunked head-major 8x8", "flags": cb.FLAG_HEAD_MAJOR, "MSDA_B200_TILE_W": 8, "MSDA_B200_TILE_H": 8}]
+            have_ref = False
         if args.only == "ctas":
             cfgs = [{"name": "default", "flags": 0}] + ctas_cfgs
             have_ref = False
