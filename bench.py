@@ -481,12 +481,18 @@ def run_b200(args):
 
 def main():
     args = parse_args()
-    if args.impl == "reference":
-        line = run_reference(args)
-    else:
-        line = run_b200(args)
+    # Exactly ONE line may reach stdout.  Libraries chat there (NCCL prints "NCCL version ..." on init), so
+    # stdout is pointed at stderr for the duration of the run and the JSON line goes to the saved descriptor.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        line = run_reference(args) if args.impl == "reference" else run_b200(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
     if line is not None:
-        print(json.dumps(line))
+        os.write(1, (json.dumps(line) + "\n").encode())
 
 
 if __name__ == "__main__":
