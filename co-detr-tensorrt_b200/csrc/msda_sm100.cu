@@ -63,6 +63,9 @@ constexpr int kThreads = 256;
 #ifndef MSDA_NB
 #define MSDA_NB 1
 #endif
+#ifndef MSDA_PIPE
+#define MSDA_PIPE 0
+#endif
 #ifndef MSDA_LB
 #define MSDA_LB 1   // levels whose row loads are issued together in the split-points path (measured: 1 is best,
                     // more registers per thread push the 450-CTA decoder grid into a second wave)
@@ -961,6 +964,86 @@ __global__ void __launch_bounds__(kThreads, (SPLIT > 1 && P_T == 4) ? MSDA_MINB_
           sm_inv = 1.f / sum;
           rfp = static_cast<const T *>(p.ref) + ((int64_t)b * p.Q + (live ? q : 0)) * p.L * p.ref_dim;
         }
+        // Software-pipelined variant (MSDA_PIPE): the row loads of sample s+1 are issued before the FMAs of
+        // sample s, across the samples of a level and across levels, so a lane always has 4-8 row loads in
+        // flight instead of 4 -> 0 -> 4.  Two row buffers (32 registers): built with 3 CTAs per SM.
+        constexpr bool kPipe = (MSDA_PIPE != 0) && !STAGE && !FUSED;
+        if constexpr (kPipe) {
+          struct InFlight {
+            uint4 r[4];
+            unsigned p0, p1;
+            float w[4];
+          };
+          // geometry of this lane's sample (point ks) of level l, from the prefetched undecoded inputs
+          auto level_geo = [&](int l, const RawSample &rw, int &gi, unsigned &gp0, unsigned &gp1, float (&gcw)[4]) {
+            float x, y, aw;
+            decode_raw<T>(rw, x, y, aw);
+            aw = live ? aw : 0.f;
+            make_geo(x, y, aw, ts.lv[l].H, ts.lv[l].W, gi, gcw);
+            gi += ts.lv[l].start;
+            gp0 = gp1 = 0u;
+            if constexpr (MATH == kFhfma) {
+              gp0 = pack_weights<T>(gcw[0], gcw[1]);
+              gp1 = pack_weights<T>(gcw[2], gcw[3]);
+            }
+          };
+          auto issue = [&](InFlight &f, int gi, unsigned gp0, unsigned gp1, const float (&gcw)[4], int k, int W) {
+            const int bi = __shfl_sync(group_mask, gi, k, G);
+            if constexpr (MATH == kFhfma) {
+              f.p0 = __shfl_sync(group_mask, gp0, k, G);
+              f.p1 = __shfl_sync(group_mask, gp1, k, G);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) f.w[j] = __shfl_sync(group_mask, gcw[j], k, G);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int idx = bi + (j & 1) + ((j & 2) ? W : 0);
+              bool on;
+              if constexpr (MATH == kFhfma) on = (((j & 2) ? f.p1 : f.p0) >> ((j & 1) * 16) & 0x7fffu) != 0u;
+              else on = f.w[j] != 0.f;
+              if (on) f.r[j] = ldg128(vm + (size_t)(unsigned)idx * pix_bytes);
+            }
+          };
+          auto consume = [&](const InFlight &f) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if constexpr (MATH == kFhfma) {
+                const unsigned w16 = (((j & 2) ? f.p1 : f.p0) >> ((j & 1) * 16)) & 0xffffu;
+                if ((w16 & 0x7fffu) != 0u) RowFma<T, kFhfma>::run(acc, f.r[j], 0.f, w16);
+              } else {
+                if (f.w[j] != 0.f) RowFma<T, kExact>::run(acc, f.r[j], f.w[j], 0u);
+              }
+            }
+          };
+          auto prefetch_after = [&](int l) {  // inputs of level l+1 of this unit, or level 0 of the next unit
+            if (l + 1 < p.L) return load_raw<T>(lp, wp, (l + 1) * 4 + ks);
+            const int64_t pn = pair_index(q_next, m_next);
+            return load_raw<T>(loc + pn * LP * 2, wgt + pn * LP, ks);
+          };
+          InFlight fa, fb;
+          int gi;
+          unsigned gp0, gp1;
+          float gcw[4];
+          level_geo(0, raw, gi, gp0, gp1, gcw);
+          raw = prefetch_after(0);
+          issue(fa, gi, gp0, gp1, gcw, 0, ts.lv[0].W);
+          for (int l = 0; l < p.L; ++l) {
+            const int W = ts.lv[l].W;
+            issue(fb, gi, gp0, gp1, gcw, 1, W);
+            consume(fa);
+            issue(fa, gi, gp0, gp1, gcw, 2, W);
+            consume(fb);
+            issue(fb, gi, gp0, gp1, gcw, 3, W);
+            consume(fa);
+            if (l + 1 < p.L) {
+              level_geo(l + 1, raw, gi, gp0, gp1, gcw);
+              raw = prefetch_after(l + 1);
+              issue(fa, gi, gp0, gp1, gcw, 0, ts.lv[l + 1].W);
+            }
+            consume(fb);
+          }
+        } else
         for (int l = 0; l < p.L; ++l) {
           const int H = ts.lv[l].H, W = ts.lv[l].W;
           float x, y, aw;
