@@ -50,6 +50,9 @@ def parse_args():
     ap.add_argument("--dtype", default=None, choices=[None, "float16", "bfloat16", "float32"])
     ap.add_argument("--loc-mode", default=None, choices=[None, "encoder", "decoder", "uniform", "adversarial"])
     ap.add_argument("--flags", type=int, default=None, help="msda_flags bit field (default: library default)")
+    ap.add_argument("--api", default="cabi", choices=["cabi", "plugin", "torch_op"],
+                    help="how the timed loop calls the library: prepared C-ABI call (default), the TensorRT-enqueue-shaped "
+                         "entry (raw pointers, external stream), or torch.ops.codetr.multi_scale_deformable_attention")
     ap.add_argument("--l2-warm", action="store_true", help="reuse ONE input set (inputs stay L2-resident); stated in config.l2_policy")
     ap.add_argument("--workspace", action="store_true", help="give the library a scratch buffer (packed-pyramid path)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -303,7 +306,23 @@ def run_b200(args):
         if args.workspace:
             need = cb.workspace_bytes(d["value"], d["sampling_loc"])
             ws = torch.empty(need, dtype=torch.uint8, device=dev) if need else None
-        calls.append(cb.PreparedForward(*(d[k] for k in keys), flags=args.flags, workspace=ws))
+        if args.api == "cabi":
+            calls.append(cb.PreparedForward(*(d[k] for k in keys), flags=args.flags, workspace=ws))
+        elif args.api == "plugin":
+            # DeformableAttentionPlugin::enqueue's calling convention: dims from descriptors, raw device pointers,
+            # caller-owned output, device-resident int64 shapes, stream passed explicitly
+            out_t = torch.empty((batch, dims["Q"], dims["M"] * dims["D"]), dtype=dt, device=dev)
+            trt_dt = {torch.float32: cb.ops.TRT_FLOAT, torch.float16: cb.ops.TRT_HALF, torch.bfloat16: cb.ops.TRT_BF16}[dt]
+            vd, ld, ptrs = tuple(d["value"].shape), tuple(d["sampling_loc"].shape), [d[k].data_ptr() for k in keys]
+
+            def plugin_call(stream_ptr, _vd=vd, _ld=ld, _ptrs=ptrs, _out=out_t, _keep=d):
+                rc = cb.plugin_enqueue(_vd, _ld, trt_dt, _ptrs, _out.data_ptr(), stream_ptr)
+                assert rc == 0, rc
+            calls.append(plugin_call)
+        else:
+            def op_call(stream_ptr, _d=d):
+                return torch.ops.codetr.multi_scale_deformable_attention(*(_d[k] for k in keys), 64)
+            calls.append(op_call)
     torch.cuda.synchronize()
 
     def barrier():
@@ -356,6 +375,18 @@ def run_b200(args):
     elapsed_ms_max = float(t.item())
     ms_per_step = elapsed_ms_max / args.steps
     images_per_s = world * batch * args.steps / (elapsed_ms_max * 1e-3)
+
+    # ---- per-call distribution (median and min of individually timed calls) ----
+    n_ind = min(200, args.steps)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_ind)]
+    for i, (e0, e1) in enumerate(evs):
+        e0.record(stream)
+        calls[i % n_sets](sptr)
+        e1.record(stream)
+    torch.cuda.synchronize()
+    per_call = sorted(1e3 * e0.elapsed_time(e1) for e0, e1 in evs)
+    per_call_us = {"median": per_call[len(per_call) // 2], "min": per_call[0], "p90": per_call[int(0.9 * (len(per_call) - 1))],
+                   "calls": n_ind, "note": "each call bracketed by its own event pair (includes event overhead)"}
 
     # ---- end-to-end leg: host buffers through msda_b200_forward_host ----
     e2e = None
@@ -465,6 +496,7 @@ def run_b200(args):
     return {
         "metric": METRIC, "value": images_per_s, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "us_per_call": ms_per_step * 1e3,
+        "per_call_us": per_call_us,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": {"float16": "f16", "bfloat16": "bf16", "float32": "f32"}[dtype_name], "data": "synthetic",
         "config": {
@@ -472,7 +504,9 @@ def run_b200(args):
             "loc_mode": args.loc_mode or wl.kind, "sharding": f"batch by image, {world} rank(s), no collective on the data path",
             "l2_policy": (f"rotating {n_sets} distinct input sets, {n_sets * hbm_bytes / 1e6:.0f} MB > 126 MB L2" if n_sets > 1
                           else "L2-WARM: one input set reused every step (not a cold-cache number)"),
-            "launch": "cuda_graph" if graph is not None else "C ABI via ctypes, back to back on one stream",
+            "launch": "cuda_graph" if graph is not None else {"cabi": "C ABI via ctypes, back to back on one stream",
+                      "plugin": "msda_b200_plugin_enqueue (TensorRT enqueue convention), back to back on one stream",
+                      "torch_op": "torch.ops.codetr.multi_scale_deformable_attention, back to back"}[args.api],
         },
         "roofline": roofline, "roofline_l2_gather": roofline_l2, "batch_sweep": batch_sweep, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
         "clocks": sampler.summary(),

@@ -471,8 +471,32 @@ def _fake(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, i
 
 
 def _op_cuda(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step):
-    return multi_scale_deformable_attention(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
-                                            im2col_step)
+    # the dispatcher's CUDA-key entry: one validation pass, one allocation, one C-ABI call
+    _validate(value, spatial_shapes, level_start_index, sampling_loc, attn_weight)
+    bs, keys, heads, chans = value.shape
+    queries, levels, points = sampling_loc.shape[1], sampling_loc.shape[3], sampling_loc.shape[4]
+    dev = value.device
+    out = torch.empty((bs, queries, heads * chans), dtype=value.dtype, device=dev)
+    ws_ptr = ws_bytes = 0
+    if _use_workspace:
+        ws_bytes = workspace_bytes(value, sampling_loc)
+        if ws_bytes:
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            ws_ptr = ws.data_ptr()
+    guard = torch.cuda.device(dev) if torch.cuda.current_device() != dev.index else None
+    if guard is not None:
+        guard.__enter__()
+    try:
+        rc = _lib.msda_b200_forward_ws(
+            value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), sampling_loc.data_ptr(),
+            attn_weight.data_ptr(), out.data_ptr(), ws_ptr, ws_bytes, bs, keys, heads, chans, levels, queries, points,
+            int(im2col_step), _DTYPES[value.dtype], _default_flags, torch.cuda.current_stream(dev).cuda_stream)
+    finally:
+        if guard is not None:
+            guard.__exit__(None, None, None)
+    if rc != 0:
+        _check(rc)
+    return out
 
 
 def _op_backward_cuda(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output, grad_value,
