@@ -570,3 +570,47 @@ def test_small_problem_kernel_matches_general_kernel(dt, cuda_device, monkeypatc
     metric = rel_l2 if dt == "f32" else max_rel
     assert metric(out.float().cpu().numpy(), ref) <= gate
     assert metric(gen.float().cpu().numpy(), ref) <= gate
+
+
+def test_degenerate_shapes_give_zeros(cuda_device):
+    """No levels or no points: the sum is empty, the output is all zeros (and still fully written)."""
+    v = torch.randn(2, 10, 8, 32, device=cuda_device, dtype=torch.float16)
+    for levels, points in ((0, 4), (2, 0)):
+        shapes = torch.tensor([[2, 3], [2, 2]][:levels], dtype=torch.int64, device=cuda_device).reshape(levels, 2)
+        lsi = torch.tensor([0, 6][:levels], dtype=torch.int64, device=cuda_device)
+        loc = torch.rand(2, 5, 8, levels, points, 2, device=cuda_device, dtype=torch.float16)
+        w = torch.rand(2, 5, 8, levels, points, device=cuda_device, dtype=torch.float16)
+        out = torch.full((2, 5, 256), float("nan"), device=cuda_device, dtype=torch.float16)
+        cb.forward_into(v, shapes, lsi, loc, w, out)
+        torch.cuda.synchronize()
+        assert torch.count_nonzero(out) == 0 and not torch.isnan(out).any()
+
+
+def test_concurrent_streams_and_threads(cuda_device):
+    """The launcher is stateless and re-entrant: two host threads, each on its own stream, interleave calls
+    (TensorRT may call enqueue from its own threads / several contexts, plugin.cpp:367)."""
+    import threading
+
+    d, _ = _small(cuda_device, torch.float16, bs=2)
+    want = cb.multi_scale_deformable_attention(*(d[k] for k in ARRAY_KEYS))
+    torch.cuda.synchronize()
+    results, errors = {}, []
+
+    def worker(i):
+        try:
+            s = torch.cuda.Stream(device=cuda_device)
+            outs = []
+            with torch.cuda.stream(s):
+                for _ in range(50):
+                    outs.append(cb.multi_scale_deformable_attention(*(d[k] for k in ARRAY_KEYS)))
+            s.synchronize()
+            results[i] = all(torch.equal(o, want) for o in outs)
+        except Exception as exc:  # pragma: no cover
+            errors.append(exc)
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors and all(results.get(i) for i in range(4))
