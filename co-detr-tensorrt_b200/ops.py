@@ -470,6 +470,15 @@ def _fake(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, i
     return value.new_empty((value.shape[0], sampling_loc.shape[1], value.shape[2] * value.shape[3]))
 
 
+def _fake_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output, grad_value,
+                   grad_sampling_loc, grad_attn_weight, im2col_step):
+    # the backward op only mutates its three gradient arguments
+    torch._check(grad_value.shape == value.shape)
+    torch._check(grad_sampling_loc.shape == sampling_loc.shape)
+    torch._check(grad_attn_weight.shape == attn_weight.shape)
+    return None
+
+
 def _op_cuda(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step):
     # the dispatcher's CUDA-key entry: one validation pass, one allocation, one C-ABI call
     _validate(value, spatial_shapes, level_start_index, sampling_loc, attn_weight)
@@ -542,6 +551,7 @@ def register_torch_op() -> None:
     lib.impl("multi_scale_deformable_attention", _op_cuda, "CUDA")
     lib.impl("multi_scale_deformable_attention_backward", _op_backward_cuda, "CUDA")
     torch.library.register_fake("codetr::multi_scale_deformable_attention", _fake, lib=lib)
+    torch.library.register_fake("codetr::multi_scale_deformable_attention_backward", _fake_backward, lib=lib)
     torch.library.register_autograd("codetr::multi_scale_deformable_attention", _autograd_backward,
                                     setup_context=_autograd_setup, lib=lib)
     _torch_lib = lib

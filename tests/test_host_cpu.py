@@ -210,3 +210,28 @@ def test_bench_reference_arm_runs_on_cpu():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "images/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_missing_native_library_fails_loudly():
+    """No CPU / PyTorch fallback: without libmsda_b200.so the package refuses to import."""
+    code = "import codetr_b200"
+    env = dict(os.environ, MSDA_B200_LIB="/nonexistent/libmsda_b200.so", PYTHONPATH=ROOT)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=ROOT)
+    assert out.returncode != 0
+    assert "NativeLibraryError" in out.stderr and "no CPU fallback" in out.stderr
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under the package, include/ or the C/CUDA sources refers to it."""
+    pkg = os.path.join(ROOT, "co-detr-tensorrt_b200")
+    offenders = []
+    for base, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cpp", ".h")):
+                txt = open(os.path.join(base, f), errors="ignore").read()
+                if re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M) or "msda_oracle" in txt or "oracle/" in txt.replace("``oracle/``", ""):
+                    offenders.append(os.path.join(base, f))
+    assert not offenders, offenders
+    code = "import sys, codetr_b200; assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules), 'oracle imported'"
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, PYTHONPATH=ROOT), cwd=ROOT)
+    assert out.returncode == 0, out.stderr

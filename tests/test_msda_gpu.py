@@ -121,8 +121,12 @@ def test_reference_forward_test(dtype, cuda_device):
     loc = torch.rand(bs, queries, heads, levels, points, 2, device=cuda_device, dtype=dtype)
     aw = torch.rand(bs, queries, heads, levels, points, device=cuda_device, dtype=dtype)
     args = (value, shapes, lsi, loc, aw, 2)
-    torch.library.opcheck(torch.ops.codetr.multi_scale_deformable_attention.default, args,
-                          test_utils=("test_schema", "test_faketensor"))
+    # the reference runs the full default opcheck suite on its op (tests:44): schema, autograd registration,
+    # fake tensor, AOT dispatch
+    torch.library.opcheck(torch.ops.codetr.multi_scale_deformable_attention.default, args)
+    if dtype == torch.float32:
+        g_args = (value.clone().requires_grad_(True), shapes, lsi, loc.clone().requires_grad_(True), aw.clone().requires_grad_(True), 2)
+        torch.library.opcheck(torch.ops.codetr.multi_scale_deformable_attention.default, g_args)
     out = torch.ops.codetr.multi_scale_deformable_attention(*args)
     ref = oracle.forward_grid_sample(value.cpu().float(), shapes.cpu(), loc.cpu().float(), aw.cpu().float())
     assert out.shape == (bs, queries, heads * dim)
