@@ -448,26 +448,25 @@ def read_bandwidth_probe(device: torch.device, working_set_bytes: int, repeats: 
 # torch.library registration: same namespace, name and schema as the reference
 # ---------------------------------------------------------------------------
 def _fake(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step):
-    # output properties of the reference's fake kernel (ops.py:59-87)
-    torch._check(value.dim() == 4)
-    torch._check(spatial_shapes.dim() == 2)
-    torch._check(level_start_index.dim() == 1)
-    torch._check(sampling_loc.dim() == 6)
-    torch._check(attn_weight.dim() == 5)
-    torch._check(value.dtype == attn_weight.dtype)
-    torch._check(value.dtype == sampling_loc.dtype)
-    torch._check(spatial_shapes.dtype == torch.int64)
-    torch._check(level_start_index.dtype == torch.int64)
+    """Meta kernel: the rank / dtype / extent agreement the reference's fake kernel asserts (ops.py:59-84) and
+    its output properties (:86-87), written as one table of conditions."""
+    ranks = ((value, 4), (spatial_shapes, 2), (level_start_index, 1), (sampling_loc, 6), (attn_weight, 5))
+    for t, r in ranks:
+        torch._check(t.dim() == r)
+    bs, _, heads, per_head = value.shape
     levels = spatial_shapes.shape[0]
-    torch._check(spatial_shapes.shape[1] == 2)
-    torch._check(level_start_index.shape[0] == levels)
-    torch._check(sampling_loc.shape[0] == value.shape[0])
-    torch._check(sampling_loc.shape[2] == value.shape[2])
-    torch._check(sampling_loc.shape[3] == levels)
-    torch._check(sampling_loc.shape[5] == 2)
+    conditions = (
+        value.dtype == attn_weight.dtype, value.dtype == sampling_loc.dtype,
+        spatial_shapes.dtype == torch.int64, level_start_index.dtype == torch.int64,
+        spatial_shapes.shape[1] == 2, level_start_index.shape[0] == levels,
+        sampling_loc.shape[0] == bs, sampling_loc.shape[2] == heads, sampling_loc.shape[3] == levels,
+        sampling_loc.shape[5] == 2,
+    )
+    for ok in conditions:
+        torch._check(ok)
     for axis in range(5):
         torch._check(attn_weight.shape[axis] == sampling_loc.shape[axis])
-    return value.new_empty((value.shape[0], sampling_loc.shape[1], value.shape[2] * value.shape[3]))
+    return value.new_empty((bs, sampling_loc.shape[1], heads * per_head))
 
 
 def _fake_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output, grad_value,

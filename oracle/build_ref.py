@@ -4,7 +4,7 @@
 
 Sources are compiled where they lie under /root/reference (nothing is copied into this repo):
   /root/reference/codetr/csrc/ms_deform_attn.cu     the reference kernel + ATen launcher, unmodified
-  oracle/ref_binding.cpp                            ~20 lines registering it as codetr_ref::...
+  oracle/ref_binding.cpp                            ~40 lines exposing it as torch.ops.codetr_ref.msda_forward / msda_backward
 with the reference's own extension flags (-O3 --use_fast_math, /root/reference/setup.py:71) and
 -gencode arch=compute_100a,code=sm_100a instead of its sm_89 default (setup.py:5-22).  The reference's
 build system (setup.py / CMake) is not run.  Output: oracle/_ref/msda_ref_cuda.so -- git-ignored, but it
@@ -49,7 +49,7 @@ def load_if_built() -> bool:
     """Load oracle/_ref/msda_ref_cuda.so if it exists; registers torch.ops.codetr_ref.*"""
     import torch
 
-    if hasattr(torch.ops, "codetr_ref") and hasattr(torch.ops.codetr_ref, "multi_scale_deformable_attention"):
+    if hasattr(torch.ops, "codetr_ref") and hasattr(torch.ops.codetr_ref, "msda_forward"):
         return True
     if not os.path.isfile(LIB_PATH):
         return False

@@ -58,7 +58,7 @@ def main():
 
             def ref():
                 rgv.zero_(); rgl.zero_(); rgw.zero_()
-                torch.ops.codetr_ref.multi_scale_deformable_attention_backward(*(d[k] for k in KEYS), go, rgv, rgl, rgw, 64)
+                torch.ops.codetr_ref.msda_backward(*(d[k] for k in KEYS), go, rgv, rgl, rgw, 64)
 
             row["reference_cuda_us"] = timeit(ref)
             ours(); ref(); torch.cuda.synchronize()

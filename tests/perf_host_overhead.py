@@ -57,7 +57,7 @@ res = {
     "python_functional_api_us": host_us(lambda: cb.multi_scale_deformable_attention(*t)),
 }
 if build_ref.load_if_built():
-    res["reference_native_op_us"] = host_us(lambda: torch.ops.codetr_ref.multi_scale_deformable_attention(*t, 64))
+    res["reference_native_op_us"] = host_us(lambda: torch.ops.codetr_ref.msda_forward(*t, 64))
 dropin = os.path.join(ROOT, "co-detr-tensorrt_b200", "csrc", "_dropin", "codetr_cpp_extension.so")
 if os.path.isfile(dropin):
     o = subprocess.run([sys.executable, __file__, "dropin", dropin], capture_output=True, text=True)

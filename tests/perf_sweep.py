@@ -224,7 +224,7 @@ def main():
             results["rows"].append(row)
             print(f"{name:24s} b{batch} {dtn:8s} {wl.kind:8s} {'fused-producers':20s} {us:9.2f} us  (L2-warm single input set)  {row['variant']}", flush=True)
         if have_ref and dtn in ("float16", "float32"):
-            fns = [(lambda s=s: torch.ops.codetr_ref.multi_scale_deformable_attention(*(s[k] for k in KEYS), 64)) for s in sets]
+            fns = [(lambda s=s: torch.ops.codetr_ref.msda_forward(*(s[k] for k in KEYS), 64)) for s in sets]
             us = time_calls(fns, max(20, iters // 2))
             row = {"workload": name, "batch": batch, "dtype": dtn, "loc_mode": loc_mode or wl.kind, "config": "reference_cuda_sm100a",
                    "variant": "codetr_ref::ms_deformable_im2col_gpu_kernel (+2 memsets, torch op overhead)", "us_per_call": us,
@@ -233,7 +233,7 @@ def main():
             print(f"{name:24s} b{batch} {dtn:8s} {row['loc_mode']:8s} {'reference_cuda':20s} {us:9.2f} us", flush=True)
             # parity of the two CUDA implementations on the same tensors (informational)
             a = cb.multi_scale_deformable_attention(*(sets[0][k] for k in KEYS)).float()
-            b = torch.ops.codetr_ref.multi_scale_deformable_attention(*(sets[0][k] for k in KEYS), 64).float()
+            b = torch.ops.codetr_ref.msda_forward(*(sets[0][k] for k in KEYS), 64).float()
             row["max_rel_vs_ours"] = float((a - b).abs().max() / b.abs().max())
         del sets
         torch.cuda.empty_cache()
