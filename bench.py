@@ -267,6 +267,9 @@ def run_b200(args):
         raise SystemExit("bench.py --impl b200 needs a CUDA device: there is no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # pinned buffers allocated below are first-touched next to the GPU when the platform exposes its NUMA node
+    # (a no-op on single-node VMs); undone before the CPU-baseline leg, which must see every host core
+    previous_affinity = cb.sharding.bind_to_gpu_numa_node(local)
     use_dist = world > 1
     if use_dist:
         import torch.distributed as dist
@@ -488,6 +491,8 @@ def run_b200(args):
         "peak_source": "msda_b200_read_probe, 48 MB working set, measured in this run",
     }
 
+    if previous_affinity:
+        os.sched_setaffinity(0, previous_affinity)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         ips, ms, cores, sample, _ = cpu_reference_leg(wl, batch, args.loc_mode, args.cpu_seconds)

@@ -235,3 +235,12 @@ def test_product_never_imports_the_oracle():
     code = "import sys, codetr_b200; assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules), 'oracle imported'"
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, PYTHONPATH=ROOT), cwd=ROOT)
     assert out.returncode == 0, out.stderr
+
+
+def test_numa_binding_is_a_safe_no_op_without_a_gpu():
+    assert sharding.gpu_numa_cpus(0) is None or isinstance(sharding.gpu_numa_cpus(0), set)
+    before = os.sched_getaffinity(0)
+    prev = sharding.bind_to_gpu_numa_node(0)
+    if prev is not None:
+        os.sched_setaffinity(0, prev)
+    assert os.sched_getaffinity(0) == before
