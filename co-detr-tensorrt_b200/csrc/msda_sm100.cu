@@ -1,44 +1,39 @@
-// msda_sm100.cu -- multi-scale deformable attention forward for NVIDIA B200 (sm_100a).
+// msda_sm100.cu -- multi-scale deformable attention for NVIDIA B200 (sm_100a): forward, opt-in
+// producer-fused forward, backward, and the C ABI of include/msda_b200.h.
 //
-// Written from scratch for Blackwell; it is NOT a port of the reference's
-// mmcv-derived kernel (codetr/csrc/ms_deform_attn.cu:211-261, one thread per
-// output channel, scalar loads).  What it computes is the reference's
-// operator, bit-for-bit in layout and boundary semantics:
+// Written from scratch for Blackwell; it is NOT a port of the reference's mmcv-derived kernels
+// (codetr/csrc/ms_deform_attn.cu: forward :211-261, one thread per output channel with scalar loads;
+// backward :263-760).  What it computes is the reference's operator, in the reference's layouts and with
+// its boundary semantics:
 //
 //   out[b,q,m,:] = sum_{l,p} w[b,q,m,l,p] * bilinear(value_l[b,:,m,:], loc[b,q,m,l,p])
 //
-// with  x_pix = x*W - 0.5,  y_pix = y*H - 0.5  (align_corners=False), zero
-// padding per corner and the whole-sample range test of
-// ms_deform_attn.cu:246-249.
+// with  x_pix = x*W - 0.5,  y_pix = y*H - 0.5  (align_corners=False), zero padding per corner and the
+// whole-sample range test of ms_deform_attn.cu:246-249.
 //
-// Design (see DESIGN.md for the measurements behind each choice)
-//   * The value pyramid is channels-last: one (pixel, head) row is D elements
-//     = 64 B in fp16/bf16 at D=32.  A *lane group* of G = D*sizeof(T)/16 lanes
-//     owns one (query, head) pair and fetches every bilinear corner row with
-//     one 128-bit load per lane (LDG.E.128); a warp therefore serves 32/G
-//     pairs per instruction instead of one.
-//   * All sample geometry (floor, corner weights, validity) is computed once
-//     per lane group, not once per channel; accumulation is fp32 (fp64 for
-//     double) and the result is rounded once on the way out.
-//   * fp16/bf16 inputs can use Blackwell's mixed-precision FMA (PTX
-//     fma.rn.f32.f16 / .bf16 -> SASS FHFMA, sm_100+ only): the 16-bit value
-//     is multiplied in place, without the unpack/convert instructions, and
-//     accumulated in fp32.
-//   * Queries are processed in spatially coherent tiles (encoder shapes,
-//     Q == S): the CTA walks a TH x TW patch of one pyramid level so that the
-//     corner rows fetched by neighbouring queries hit L1/L2; in "head-major"
-//     order a warp holds the same head of 32/G neighbouring queries, so
-//     samples that land on the same pixel coalesce into one L1 wavefront.
-//   * Level shapes / start indices stay device-resident (TensorRT hands them
-//     over as device buffers, deformable_attention_plugin.cpp:339-341): the
-//     kernel reads them itself, the launcher never touches them, so the launch
-//     is capture-safe and sync-free.
-//   * Per-query sampling locations and weights are staged into shared memory
-//     with 1-D TMA bulk copies (cp.async.bulk + mbarrier, SASS UBLKCP) when the
-//     tile's rows are 16-byte aligned; otherwise they are read directly.
-//   * Tensor cores are not used: the op is a gather plus a weighted sum.
+// Kernels (DESIGN.md section 4 has the measurements behind every choice, including the ones that lost)
+//   msda_fwd_vec      the hot kernel.  A lane group of G = D*sizeof(T)/16 lanes owns one (query, head)
+//                     pair and fetches each 64-byte corner row with one LDG.E.128 per lane; lane k of the
+//                     group works out the geometry of point k of the level once and broadcasts it by
+//                     shuffle; every "does not contribute" case is a weight of exactly zero, which
+//                     predicates off the load and the FMAs; fp16 multiplies in place with Blackwell's
+//                     mixed-precision FMA (PTX fma.rn.f32.f16 -> SASS FHFMA) and accumulates in fp32; the
+//                     grid is persistent (resident CTA count) and the next unit's first sample is loaded
+//                     while the current one is computed.  Template switches: P (4 or run-time), SPLIT
+//                     (points dealt to 2/4 lane groups), MATH (fhfma / exact), STAGE (TMA bulk-copy staging
+//                     of locations and weights, opt-in), FUSED (softmax + location arithmetic in-kernel).
+//   msda_fwd_small    decoder-sized launches: 4-way point split, 128-thread CTAs, level table held in
+//                     lanes, no shared memory, no barrier.
+//   msda_pack_value + msda_fwd_packed   opt-in packed-pyramid path: 128-byte (pixel, head) entries that also
+//                     hold the right-hand neighbour, fetched with 256-bit loads (LDG.E.256, sm_100+).
+//   msda_fwd_generic  any shape / any dtype (incl. fp64), one thread per output element.
+//   msda_bwd_vec / msda_bwd_generic     backward; grad_value scattered with 16-byte vector reductions
+//                     (red.global.add.v4.f32 / .noftz.v4.f16x2 -> SASS REDG.E.ADD.F16x8).
+//   read_probe_kernel L2 / HBM read-bandwidth probe for the roofline denominators.
 //
-// The C ABI is declared in include/msda_b200.h.
+// Level shapes / start indices stay device-resident (TensorRT hands them over as device buffers,
+// deformable_attention_plugin.cpp:339-341): the kernels read them, the launcher never does, so every entry
+// point is capture-safe and sync-free.  Tensor cores are not used: the op is a gather plus a weighted sum.
 
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
