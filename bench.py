@@ -509,7 +509,7 @@ def run_b200(args):
             "loc_mode": args.loc_mode or wl.kind, "sharding": f"batch by image, {world} rank(s), no collective on the data path",
             "l2_policy": (f"rotating {n_sets} distinct input sets, {n_sets * hbm_bytes / 1e6:.0f} MB > 126 MB L2" if n_sets > 1
                           else "L2-WARM: one input set reused every step (not a cold-cache number)"),
-            "launch": "cuda_graph" if graph is not None else {"cabi": "C ABI via ctypes, back to back on one stream",
+            "launch": "cuda_graph" if graph is not None else {"cabi": "C ABI via ctypes, back to back on one stream (launches carry the programmatic-stream-serialization attribute; reads wait for the previous kernel)",
                       "plugin": "msda_b200_plugin_enqueue (TensorRT enqueue convention), back to back on one stream",
                       "torch_op": "torch.ops.codetr.multi_scale_deformable_attention, back to back"}[args.api],
         },

@@ -60,6 +60,7 @@ FLAG_NO_STAGING = 1 << 4
 FLAG_STAGE_TMA = 1 << 5
 FLAG_NO_PACKED = 1 << 6
 FLAG_HEAD_MAJOR = 1 << 7
+FLAG_PDL = 1 << 8
 
 
 class NativeLibraryError(RuntimeError):

@@ -127,6 +127,7 @@ struct MsdaParams {
   int want_tiled;       // 1: use 2-D tiles when sum(H*W) == Q
   int head_major;       // 1: a warp holds one head of 32/G neighbouring queries
   int chunked;          // 1: each CTA owns a contiguous run of (tile, pass) units instead of a strided set
+  int pdl_early_tables; // 1: (MSDA_FLAG_PDL) read the level tables before waiting for the preceding kernel
 };
 
 struct LevelGeom {
@@ -602,6 +603,12 @@ __device__ __forceinline__ unsigned pack_weights<float>(float, float) {
   return 0u;
 }
 
+// ---- programmatic dependent launch (PDL): let the next kernel of the stream start its prologue while this
+// one drains, and hold this kernel's data reads until the previous kernel has completed.  Both are no-ops
+// unless the launch carried cudaLaunchAttributeProgrammaticStreamSerialization.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait_prior_grid() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- TMA 1-D bulk copy + mbarrier (Blackwell/Hopper async proxy) ----
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -783,6 +790,10 @@ __global__ void __launch_bounds__(kThreads, (SPLIT > 1 && P_T == 4) ? MSDA_MINB_
   __shared__ TileSetup ts;
   __shared__ __align__(8) uint64_t stage_bar[2];
   extern __shared__ __align__(128) unsigned char stage_mem[];  // STAGE: 2 x (qpp loc rows + qpp weight rows)
+  // PDL: the level table (constant for a model / engine) is read before waiting for the preceding kernel;
+  // everything that kernel may have produced (value, locations, weights) is read after the wait.
+  pdl_launch_dependents();
+  if (!p.pdl_early_tables) pdl_wait_prior_grid();  // default: nothing at all is read before the preceding kernel is done
   if (threadIdx.x < 32) setup_tiles(p, ts);
   if constexpr (STAGE) {
     if (threadIdx.x == 32) {
@@ -792,6 +803,7 @@ __global__ void __launch_bounds__(kThreads, (SPLIT > 1 && P_T == 4) ? MSDA_MINB_
     }
   }
   __syncthreads();
+  if (p.pdl_early_tables) pdl_wait_prior_grid();
 
   const char *__restrict__ value = static_cast<const char *>(p.value);
   // fused mode: "loc" are the raw sampling offsets and "wgt" the pre-softmax logits (same layouts)
@@ -1231,6 +1243,8 @@ __global__ void __launch_bounds__(kSmallThreads, 8) msda_fwd_small(const MsdaPar
   const int M = p.M, LP = p.L * 4;
   const unsigned pix_bytes = (unsigned)(M * D * E);
 
+  pdl_launch_dependents();
+  if (!p.pdl_early_tables) pdl_wait_prior_grid();
   // level table: lane l holds level l (L <= 32 guaranteed by the host)
   int lvH = 0, lvW = 0, lvS = 0;
   if (lane < p.L) {
@@ -1238,6 +1252,7 @@ __global__ void __launch_bounds__(kSmallThreads, 8) msda_fwd_small(const MsdaPar
     lvW = (int)__ldg(p.shapes + 2 * lane + 1);
     lvS = (int)__ldg(p.starts + lane);
   }
+  if (p.pdl_early_tables) pdl_wait_prior_grid();  // value / locations / weights may come from the preceding kernel
 
   const int64_t pairs = (int64_t)p.B * p.Q * M;
   const int64_t pr = ((int64_t)blockIdx.x * kSmallThreads + threadIdx.x) / GS;
@@ -1816,11 +1831,30 @@ int launch_generic(const MsdaParams &p, cudaStream_t stream) {
   return (int)cudaGetLastError();
 }
 
+// Launch with or without the programmatic-stream-serialization attribute.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl,
+                          Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 struct VecPlan {
   int split;
   int math;
   unsigned grid, grid_y;
   unsigned stage_bytes;  // dynamic shared memory of the TMA staging buffers, 0 = direct loads
+  bool pdl;              // launch with programmatic stream serialization (MSDA_FLAG_PDL)
 };
 
 template <typename T, int D, int P_T, int SPLIT, int MATH>
@@ -1838,9 +1872,10 @@ int launch_vec_inst(const MsdaParams &p, const VecPlan &plan, cudaStream_t strea
       return (int)cudaGetLastError();
     }
   }
-  msda_fwd_vec<T, D, P_T, SPLIT, MATH, false><<<dim3(plan.grid, plan.grid_y, 1), kThreads, 0, stream>>>(p);
+  const cudaError_t le = launch_kernel(msda_fwd_vec<T, D, P_T, SPLIT, MATH, false, false>, dim3(plan.grid, plan.grid_y, 1),
+                                       dim3(kThreads), 0, stream, plan.pdl, p);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
-  return (int)cudaGetLastError();
+  return le != cudaSuccess ? (int)le : (int)cudaGetLastError();
 }
 
 template <typename T, int D, int MATH>
@@ -1935,6 +1970,12 @@ int forward_impl(MsdaParams p, int dtype, unsigned flags, void *workspace, size_
   // fp16 defaults to the FHFMA path (combined weights rounded to fp16: measured max-normalised error
   // 4.7e-4 vs 2.7e-4 for fp32 weights at the headline shape, gate 2e-3); bf16 weights would keep only 8
   // bits, so bf16 defaults to fp32 weights
+  // Programmatic dependent launch is on by default in its conservative form: this kernel's CTAs may be
+  // scheduled while the preceding kernel of the stream drains (hides launch latency and fills its tail),
+  // but every thread waits for that kernel to complete before it reads anything.  MSDA_FLAG_PDL additionally
+  // reads the two level tables before the wait.  MSDA_B200_PDL=0 turns the attribute off.
+  plan.pdl = env_int("MSDA_B200_PDL", 1) != 0;
+  p.pdl_early_tables = (plan.pdl && (flags & MSDA_FLAG_PDL)) ? 1 : 0;
   plan.math = (dtype == MSDA_F16) ? kFhfma : kExact;
   if (E == 2) {
     if (flags & MSDA_FLAG_MATH_FHFMA) plan.math = kFhfma;
@@ -2027,9 +2068,9 @@ int forward_impl(MsdaParams p, int dtype, unsigned flags, void *workspace, size_
       constexpr int DD = decltype(tag_d)::value;
       if constexpr (DD * (int)sizeof(TT) / 16 * 4 <= 32) {
         if (sizeof(TT) == 2 && plan.math == kFhfma) {
-          if constexpr (sizeof(TT) == 2) msda_fwd_small<TT, DD, kFhfma><<<sgrid, kSmallThreads, 0, stream>>>(p);
+          if constexpr (sizeof(TT) == 2) launch_kernel(msda_fwd_small<TT, DD, kFhfma>, dim3(sgrid), dim3(kSmallThreads), 0, stream, plan.pdl, p);
         } else {
-          msda_fwd_small<TT, DD, kExact><<<sgrid, kSmallThreads, 0, stream>>>(p);
+          launch_kernel(msda_fwd_small<TT, DD, kExact>, dim3(sgrid), dim3(kSmallThreads), 0, stream, plan.pdl, p);
         }
         g_launch_count.fetch_add(1, std::memory_order_relaxed);
         rc3 = (int)cudaGetLastError();

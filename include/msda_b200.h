@@ -74,7 +74,13 @@ enum msda_flags {
   MSDA_FLAG_STAGE_TMA = 1 << 5,     /* stage loc/weights of each pass with TMA bulk copies (opt-in:
                                        measured slightly slower than direct loads) */
   MSDA_FLAG_NO_PACKED = 1 << 6,     /* ignore the workspace: never use the packed-pyramid path */
-  MSDA_FLAG_HEAD_MAJOR = 1 << 7     /* a warp holds one head of neighbouring queries (default: query-major) */
+  MSDA_FLAG_HEAD_MAJOR = 1 << 7,    /* a warp holds one head of neighbouring queries (default: query-major) */
+  MSDA_FLAG_PDL = 1 << 8            /* The launches always carry the programmatic-stream-serialization attribute
+                                       (CTAs may be scheduled while the preceding kernel of the stream drains; all
+                                       reads wait for that kernel -- semantics are plain stream order).  This flag
+                                       additionally lets the kernel read spatial_shapes / level_start_index BEFORE
+                                       that wait: only set it if the two level tables are not produced by the
+                                       immediately preceding kernel (they are constants in every known caller). */
 };
 
 /*
