@@ -1862,14 +1862,16 @@ int launch_vec_inst(const MsdaParams &p, const VecPlan &plan, cudaStream_t strea
   constexpr int G = D * (int)sizeof(T) / 16;
   if constexpr (P_T == 4 && SPLIT == 1 && G >= 4) {
     if (p.ref_dim != 0) {
-      msda_fwd_vec<T, D, P_T, SPLIT, MATH, false, true><<<dim3(plan.grid, plan.grid_y, 1), kThreads, 0, stream>>>(p);
+      const cudaError_t fe = launch_kernel(msda_fwd_vec<T, D, P_T, SPLIT, MATH, false, true>, dim3(plan.grid, plan.grid_y, 1),
+                                           dim3(kThreads), 0, stream, plan.pdl, p);
       g_launch_count.fetch_add(1, std::memory_order_relaxed);
-      return (int)cudaGetLastError();
+      return fe != cudaSuccess ? (int)fe : (int)cudaGetLastError();
     }
     if (plan.stage_bytes > 0) {
-      msda_fwd_vec<T, D, P_T, SPLIT, MATH, true><<<dim3(plan.grid, plan.grid_y, 1), kThreads, plan.stage_bytes, stream>>>(p);
+      const cudaError_t se = launch_kernel(msda_fwd_vec<T, D, P_T, SPLIT, MATH, true, false>, dim3(plan.grid, plan.grid_y, 1),
+                                           dim3(kThreads), plan.stage_bytes, stream, plan.pdl, p);
       g_launch_count.fetch_add(1, std::memory_order_relaxed);
-      return (int)cudaGetLastError();
+      return se != cudaSuccess ? (int)se : (int)cudaGetLastError();
     }
   }
   const cudaError_t le = launch_kernel(msda_fwd_vec<T, D, P_T, SPLIT, MATH, false, false>, dim3(plan.grid, plan.grid_y, 1),
