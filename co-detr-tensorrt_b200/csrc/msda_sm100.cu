@@ -2060,8 +2060,17 @@ int forward_impl(MsdaParams p, int dtype, unsigned flags, void *workspace, size_
   plan.grid = (unsigned)grid;
   plan.grid_y = (unsigned)p.B;
 
+  // PDL pays when the grid fills the machine (its CTAs can only land where the previous kernel's exit) or on
+  // the small-problem kernel; a partial grid placed early piles onto the first SMs that free up and runs
+  // unbalanced (measured: 1,900-query decoder 12.6 -> 14.5 us), so it is launched the plain way.
+  const bool small_kernel = plan.split == 4 && !fused && p.P == 4 && p.L <= 8 && env_int("MSDA_B200_SMALL", 1);
+  if (!small_kernel && (int64_t)plan.grid * plan.grid_y < (int64_t)sms * MSDA_MINB) {
+    plan.pdl = false;
+    p.pdl_early_tables = 0;
+  }
+
   // ---- small-problem kernel (decoder): 4-way point split, no tiles, no barrier ----
-  if (plan.split == 4 && !fused && p.P == 4 && p.L <= 8 && env_int("MSDA_B200_SMALL", 1)) {
+  if (small_kernel) {
     const int64_t lanes = pairs * G * 4;
     const unsigned sgrid = (unsigned)((lanes + kSmallThreads - 1) / kSmallThreads);
     int rc3 = MSDA_ERR_UNSUPPORTED;
