@@ -104,6 +104,37 @@ def build_native(force: bool = False, verbose: bool = False, extra_flags: Option
     return LIB_PATH
 
 
+TORCH_BINDING_DIR = os.path.join(CSRC_DIR, "_torch")
+TORCH_BINDING_PATH = os.path.join(TORCH_BINDING_DIR, "codetr_b200_torch.so")
+TORCH_BINDING_SOURCES = [os.path.join(CSRC_DIR, "codetr_torch_binding.cpp"), os.path.join(CSRC_DIR, "codetr_aten_adapter.cpp")]
+
+
+def build_torch_binding(force: bool = False, verbose: bool = False) -> str:
+    """Compile the optional native operator registration (codetr_torch_binding.cpp + the ATen adapter) in-tree
+    with torch.utils.cpp_extension; links libmsda_b200.so through an $ORIGIN-relative rpath."""
+    build_native()
+    if not force and os.path.isfile(TORCH_BINDING_PATH) and all(
+            os.path.getmtime(TORCH_BINDING_PATH) > os.path.getmtime(f) for f in TORCH_BINDING_SOURCES + HEADERS):
+        return TORCH_BINDING_PATH
+    os.makedirs(TORCH_BINDING_DIR, exist_ok=True)
+    env_backup = {k: os.environ.get(k) for k in ("CC", "CXX", "TORCH_CUDA_ARCH_LIST")}
+    os.environ["CC"], os.environ["CXX"] = "/usr/bin/gcc", "/usr/bin/g++"
+    os.environ["TORCH_CUDA_ARCH_LIST"] = "10.0a"
+    try:
+        from torch.utils.cpp_extension import load
+
+        load(name="codetr_b200_torch", sources=TORCH_BINDING_SOURCES, extra_cflags=["-O2"],
+             extra_include_paths=[INCLUDE_DIR], extra_ldflags=[f"-L{CSRC_DIR}", "-lmsda_b200", "-Wl,-rpath,\\$$ORIGIN/.."],
+             build_directory=TORCH_BINDING_DIR, is_python_module=False, with_cuda=True, verbose=verbose)
+    finally:
+        for k, v in env_backup.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    return TORCH_BINDING_PATH
+
+
 _lib: Optional[ctypes.CDLL] = None
 
 

@@ -532,23 +532,43 @@ def _autograd_setup(ctx, inputs, output):
 
 
 _torch_lib = None
+op_registration = "none"   # "native" (codetr_b200_torch.so), "python", or "external" (someone else defined codetr::)
 
 
 def register_torch_op() -> None:
-    """Define ``codetr::multi_scale_deformable_attention`` unless a library that already defines it
-    (the reference's own ``codetr_cpp_extension.so``, or our ATen adapter build) is loaded."""
-    global _torch_lib
+    """Make ``torch.ops.codetr.multi_scale_deformable_attention`` (+ ``_backward``) available.
+
+    Preference order: (1) a library that already defines the namespace (the reference's own
+    ``codetr_cpp_extension.so`` or the drop-in build) is left alone; (2) the package's optional native
+    registration ``csrc/_torch/codetr_b200_torch.so`` (7 us of host time per call) unless
+    ``MSDA_B200_PYTHON_OP=1``; (3) registration from Python (26 us per call; needs nothing but the C-ABI
+    library).  The fake kernels and the autograd glue are registered from Python in cases (2) and (3)."""
+    global _torch_lib, op_registration
     if _torch_lib is not None:
         return
+    import os
+
     already = hasattr(torch.ops, "codetr") and hasattr(torch.ops.codetr, "multi_scale_deformable_attention")
     if already:
-        _torch_lib = False
+        _torch_lib, op_registration = False, "external"
         return
-    lib = torch.library.Library("codetr", "DEF")
-    lib.define(OP_SCHEMA)
-    lib.define(BACKWARD_SCHEMA)
-    lib.impl("multi_scale_deformable_attention", _op_cuda, "CUDA")
-    lib.impl("multi_scale_deformable_attention_backward", _op_backward_cuda, "CUDA")
+    native = _native.TORCH_BINDING_PATH
+    if os.path.isfile(native) and os.environ.get("MSDA_B200_PYTHON_OP", "0") != "1":
+        try:
+            torch.ops.load_library(native)
+            lib = torch.library.Library("codetr", "FRAGMENT")
+            op_registration = "native"
+        except Exception:  # stale / incompatible build: fall through to the Python registration
+            lib = None
+    else:
+        lib = None
+    if lib is None:
+        lib = torch.library.Library("codetr", "DEF")
+        lib.define(OP_SCHEMA)
+        lib.define(BACKWARD_SCHEMA)
+        lib.impl("multi_scale_deformable_attention", _op_cuda, "CUDA")
+        lib.impl("multi_scale_deformable_attention_backward", _op_backward_cuda, "CUDA")
+        op_registration = "python"
     torch.library.register_fake("codetr::multi_scale_deformable_attention", _fake, lib=lib)
     torch.library.register_fake("codetr::multi_scale_deformable_attention_backward", _fake_backward, lib=lib)
     torch.library.register_autograd("codetr::multi_scale_deformable_attention", _autograd_backward,

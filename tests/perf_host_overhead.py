@@ -1,6 +1,6 @@
 """Host-side cost per call of each binding (manual, GPU box).  Tiny tensors, so the GPU is never the limit:
 the figure is CPU microseconds per call through (a) the prepared C-ABI call, (b) the plugin-enqueue-shaped
-entry, (c) the Python-registered torch op, (d) the drop-in native extension (the reference's own binding file
+entry, (c) the package's torch op (native or Python registration, whichever is active; run again with MSDA_B200_PYTHON_OP=1 for the other), (d) the drop-in native extension (the reference's own binding file
 linked against this repo's adapter; separate process), (e) the reference's own extension (oracle/_ref)."""
 import os
 import subprocess
@@ -53,7 +53,7 @@ ptrs = [x.data_ptr() for x in t]
 res = {
     "prepared_cabi_call_us": host_us(lambda: prep(stream)),
     "plugin_enqueue_entry_us": host_us(lambda: cb.plugin_enqueue(t[0].shape, t[3].shape, 1, ptrs, out.data_ptr(), stream)),
-    "python_torch_op_us": host_us(lambda: torch.ops.codetr.multi_scale_deformable_attention(*t, 64)),
+    f"torch_op_{cb.ops.op_registration}_registration_us": host_us(lambda: torch.ops.codetr.multi_scale_deformable_attention(*t, 64)),
     "python_functional_api_us": host_us(lambda: cb.multi_scale_deformable_attention(*t)),
 }
 if build_ref.load_if_built():

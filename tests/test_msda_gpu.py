@@ -518,13 +518,13 @@ def test_packed_path_exotic_level_layout_falls_back(cuda_device, monkeypatch):
 
 
 def test_packed_path_full_size_and_torch_op(cuda_device):
-    """Headline shape: the registered torch op hands the library a scratch buffer and gets the packed path;
+    """Headline shape: with workspaces enabled the package hands the library a scratch buffer and gets the packed path;
     bits equal the direct path; the plugin-style call with a TensorRT workspace does the same."""
     arrs = _full_inputs(W.HEADLINE, 1)
     d = to_dev(arrs, torch.float16, cuda_device)
-    old = cb.set_use_workspace(True)
+    old = cb.set_use_workspace(True)   # honoured by the package's functional API and its Python-registered op
     try:
-        out = torch.ops.codetr.multi_scale_deformable_attention(*(d[k] for k in ARRAY_KEYS), 64)
+        out = cb.multi_scale_deformable_attention(*(d[k] for k in ARRAY_KEYS), 64)
         variant = cb.last_variant()
     finally:
         cb.set_use_workspace(old)
@@ -645,3 +645,32 @@ def test_programmatic_dependent_launch_keeps_stream_order(name, cuda_device):
     pdl = chain(cb.FLAG_PDL)
     for a, b in zip(plain, pdl):
         assert torch.equal(a, b)
+
+
+def test_python_registered_op_path_in_fresh_process(cuda_device):
+    """The operators can be registered natively (csrc/_torch/codetr_b200_torch.so, the default when built) or
+    from Python (MSDA_B200_PYTHON_OP=1).  The rest of this file runs on whichever is the default; this test
+    runs the core operator checks on the Python registration in a fresh process."""
+    import subprocess, sys
+
+    code = """
+import os, sys, numpy as np, torch
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import codetr_b200 as cb, oracle
+assert cb.ops.op_registration == "python", cb.ops.op_registration
+z = np.load(os.path.join(ROOT, "tests", "golden", "codino_dec_tiny.npz"))
+dev = lambda k, dt=None: (torch.from_numpy(z[k]).cuda() if dt is None else torch.from_numpy(z[k]).cuda().to(dt))
+args = (dev("value"), dev("spatial_shapes"), dev("level_start_index"), dev("sampling_loc"), dev("attn_weight"), 64)
+torch.library.opcheck(torch.ops.codetr.multi_scale_deformable_attention.default, args)
+out = torch.ops.codetr.multi_scale_deformable_attention(*args)
+ref = z["out_f32"]
+assert np.linalg.norm(out.cpu().numpy() - ref) / np.linalg.norm(ref) <= 1e-5
+v = dev("value").double().requires_grad_(True)
+o = torch.ops.codetr.multi_scale_deformable_attention(v, args[1], args[2], dev("sampling_loc").double(), dev("attn_weight").double(), 64)
+o.backward(torch.from_numpy(z["grad_out"]).cuda())
+assert float((v.grad.cpu() - torch.from_numpy(z["grad_value"])).abs().max()) < 1e-10
+print("PYTHON_OP_OK")
+"""
+    env = dict(os.environ, MSDA_B200_PYTHON_OP="1")
+    out = subprocess.run([sys.executable, "-c", f"ROOT = {os.path.dirname(GOLDEN)[:-6]!r}\n" + code], capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0 and "PYTHON_OP_OK" in out.stdout, out.stdout + out.stderr
