@@ -104,6 +104,15 @@ struct Elem<__nv_bfloat16> {
 };
 
 // ---------------------------------------------------------------------------
+// Dynamic unit scheduling.  Each launch that uses it owns one {next, done} counter pair out of this pool
+// (picked round-robin on the host).  Warps draw (tile, pass, warp-slice) units with atomicAdd(next); the last
+// warp of the grid to run dry resets the pair, so the pool needs no host-side memset and stays zero between
+// launches.  Not used under stream capture (a replayed graph would share its slot with itself).
+// ---------------------------------------------------------------------------
+constexpr int kSchedSlots = 4096;
+__device__ unsigned g_sched[kSchedSlots][2];
+
+// ---------------------------------------------------------------------------
 // kernel parameters
 // ---------------------------------------------------------------------------
 struct MsdaParams {
@@ -128,6 +137,7 @@ struct MsdaParams {
   int head_major;       // 1: a warp holds one head of 32/G neighbouring queries
   int chunked;          // 1: each CTA owns a contiguous run of (tile, pass) units instead of a strided set
   int pdl_early_tables; // 1: (MSDA_FLAG_PDL) read the level tables before waiting for the preceding kernel
+  unsigned *sched;      // dynamic unit scheduling: {next warp-unit, finished warps} counters of this launch, or nullptr
 };
 
 struct LevelGeom {
@@ -776,8 +786,9 @@ __device__ __forceinline__ void pass_query_range(const MsdaParams &p, const Tile
 //         (small-Q / decoder shapes, to expose more parallelism)
 //   MATH  kExact: fp32 weights ; kFhfma: 16-bit weights + FHFMA
 // ---------------------------------------------------------------------------
-template <typename T, int D, int P_T, int SPLIT, int MATH, bool STAGE, bool FUSED = false>
+template <typename T, int D, int P_T, int SPLIT, int MATH, bool STAGE, bool FUSED = false, bool DYN = false>
 __global__ void __launch_bounds__(kThreads, (SPLIT > 1 && P_T == 4) ? MSDA_MINB_SPLIT : MSDA_MINB) msda_fwd_vec(const MsdaParams p) {
+  static_assert(!(DYN && STAGE), "shared-memory staging needs CTA-wide units");
   constexpr int E = (int)sizeof(T);
   constexpr int VEC = 16 / E;            // channels per lane
   constexpr int G = D / VEC;             // lanes per corner row
@@ -824,19 +835,22 @@ __global__ void __launch_bounds__(kThreads, (SPLIT > 1 && P_T == 4) ? MSDA_MINB_
   const int total = ts.n_tiles * p.passes;
   const int b = blockIdx.y;
 
-  // When a pass is a whole number of queries (qpp > 0) the slot -> (query-in-pass, head) map does not
-  // depend on the pass and is worked out once.
-  const int ls = (int)(threadIdx.x / GS);
-  int tql = 0, m_fixed = 0;
-  if (p.qpp) {
+  // A pass is split over the CTA's warps: warp-slice k of a pass holds slots [k*32/GS, (k+1)*32/GS).  With
+  // static scheduling k is the warp's own index; with dynamic scheduling (DYN) a warp draws (pass, k) units.
+  constexpr int WPC = kThreads / 32;
+  const int lane_slot = (int)((threadIdx.x & 31) / GS);
+  // slot -> (query-in-pass, head) when a pass is a whole number of queries (qpp > 0)
+  auto slot_map = [&](int ls, int &tql_out, int &m_out) {
     if (p.head_major) {
       const int g = ls & (PPW - 1);
-      const int qb = fast_div(ls / PPW, M, p.inv_M, m_fixed);
-      tql = qb * PPW + g;
+      const int qb = fast_div(ls / PPW, M, p.inv_M, m_out);
+      tql_out = qb * PPW + g;
     } else {
-      tql = fast_div(ls, M, p.inv_M, m_fixed);
+      tql_out = fast_div(ls, M, p.inv_M, m_out);
     }
-  }
+  };
+  int tql = 0, m_fixed = 0;  // static scheduling: this thread's fixed slot
+  if (p.qpp) slot_map((int)(threadIdx.x / GS), tql, m_fixed);
 
   // STAGE: the locations / weights of the pass's queries are copied into shared memory by 1-D TMA bulk
   // copies (one padded row per query, so the lane groups of a warp read distinct banks), double
@@ -859,14 +873,17 @@ __global__ void __launch_bounds__(kThreads, (SPLIT > 1 && P_T == 4) ? MSDA_MINB_
     }
   };
 
-  // (tile, pass) unit -> this lane group's query (or -1 for a padding slot) and head
-  auto decode_unit = [&](int w, int &q, int &m) {
+  // (tile, pass) unit w, warp-slice k -> this lane group's query (or -1 for a padding slot) and head
+  auto decode_unit = [&](int w, int k, int &q, int &m) {
     int pass;
     const int t = fast_div(w, p.passes, p.inv_passes, pass);
+    const int ls = k * (32 / GS) + lane_slot;
     int tq;
     if (p.qpp) {
-      tq = pass * p.qpp + tql;
+      int tq_local = tql;
       m = m_fixed;
+      if constexpr (DYN) slot_map(ls, tq_local, m);
+      tq = pass * p.qpp + tq_local;
       q = tile_query(p, ts, t, tq);
     } else {
       const int s = pass * PAIRS_PER_PASS + ls;
@@ -903,8 +920,25 @@ __global__ void __launch_bounds__(kThreads, (SPLIT > 1 && P_T == 4) ? MSDA_MINB_
     w_end = total;
     w_step = gridDim.x;
   }
-  if (w_begin < w_end) {
-    decode_unit(w_begin, q, m);
+  // DYN: warp-units are drawn from the launch's counter; lane 0 draws, the warp shares the value
+  const int warp_id = (int)(threadIdx.x >> 5);
+  const int total_wu = total * WPC;
+  unsigned *const sched = p.sched + (size_t)blockIdx.y * 2;  // one counter pair per image (grid.y)
+  auto draw = [&]() -> int {
+    unsigned v = 0;
+    if ((threadIdx.x & 31) == 0) v = atomicAdd(sched, 1u);
+    return (int)__shfl_sync(0xffffffffu, v, 0);
+  };
+  int w = w_begin, k = warp_id;
+  bool have = w_begin < w_end;
+  if constexpr (DYN) {
+    const int wu = draw();
+    have = wu < total_wu;
+    w = wu / WPC;
+    k = wu % WPC;
+  }
+  if (have) {
+    decode_unit(w, k, q, m);
     if constexpr (kCarry) {
       const int64_t pr = pair_index(q, m);
       carry = load_raw<T>(loc + pr * LP * 2, wgt + pr * LP, sub & 3);
@@ -915,14 +949,24 @@ __global__ void __launch_bounds__(kThreads, (SPLIT > 1 && P_T == 4) ? MSDA_MINB_
   }
 
   int it = 0;
-  for (int w = w_begin; w < w_end; w += w_step, ++it) {
+  while (have) {
+    // the unit after this one (static: arithmetic; dynamic: drawn now, so the atomic's latency hides behind
+    // the work of the current unit)
+    int w_next = w + w_step, k_next = k;
+    bool have_next = w_next < w_end;
+    if constexpr (DYN) {
+      const int wu = draw();
+      have_next = wu < total_wu;
+      w_next = wu / WPC;
+      k_next = wu % WPC;
+    }
     int q_next = -1, m_next = m;
-    if (w + w_step < w_end) decode_unit(w + w_step, q_next, m_next);
+    if (have_next) decode_unit(w_next, k_next, q_next, m_next);
     const unsigned char *slp = nullptr, *swp = nullptr;
     if constexpr (STAGE) {
       const int buf = it & 1;
       __syncthreads();  // every thread has finished reading buffer buf^1 (previous pass)
-      if (threadIdx.x == 0 && w + w_step < w_end) stage_issue(w + w_step, buf ^ 1);
+      if (threadIdx.x == 0 && have_next) stage_issue(w_next, buf ^ 1);
       mbar_wait(&stage_bar[buf], (unsigned)((it >> 1) & 1));
       slp = stage_mem + buf * stage_buf_bytes + tql * p.stage_loc_row + m * (LP * 2 * E);
       swp = stage_mem + buf * stage_buf_bytes + p.qpp * p.stage_loc_row + tql * p.stage_w_row + m * (LP * E);
@@ -1217,6 +1261,21 @@ __global__ void __launch_bounds__(kThreads, (SPLIT > 1 && P_T == 4) ? MSDA_MINB_
     }
     q = q_next;
     m = m_next;
+    w = w_next;
+    k = k_next;
+    have = have_next;
+    ++it;
+  }
+  if constexpr (DYN) {
+    // this warp has drawn its last unit; the last warp of the image's grid row to get here re-arms the counters
+    if ((threadIdx.x & 31) == 0) {
+      const unsigned finished = atomicAdd(sched + 1, 1u);
+      if (finished == gridDim.x * WPC - 1) {
+        sched[0] = 0u;
+        sched[1] = 0u;
+        __threadfence();
+      }
+    }
   }
 }
 
@@ -1813,6 +1872,26 @@ int sm_count() {
   return cached[dev];
 }
 
+// Counter pairs for one launch with dynamic unit scheduling (one pair per image), or nullptr when the pool
+// cannot be used: symbol lookup failed, more images than a slot run holds, or the stream is being captured.
+unsigned *sched_slots(int images, cudaStream_t stream) {
+  constexpr int kMaxImages = 64;
+  if (images > kMaxImages) return nullptr;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) return nullptr;
+  static unsigned *base[64] = {nullptr};
+  static std::atomic<unsigned> next{0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (!base[dev]) {
+    void *ptr = nullptr;
+    if (cudaGetSymbolAddress(&ptr, g_sched) != cudaSuccess) return nullptr;
+    base[dev] = static_cast<unsigned *>(ptr);
+  }
+  const unsigned first = next.fetch_add((unsigned)images, std::memory_order_relaxed) % (unsigned)(kSchedSlots - kMaxImages);
+  return base[dev] + (size_t)first * 2;
+}
+
 int env_int(const char *name, int fallback) {
   const char *v = getenv(name);
   if (!v || !*v) return fallback;
@@ -1855,6 +1934,7 @@ struct VecPlan {
   unsigned grid, grid_y;
   unsigned stage_bytes;  // dynamic shared memory of the TMA staging buffers, 0 = direct loads
   bool pdl;              // launch with programmatic stream serialization (MSDA_FLAG_PDL)
+  bool dyn;              // warps draw their units from a device counter (p.sched) instead of striding
 };
 
 template <typename T, int D, int P_T, int SPLIT, int MATH>
@@ -1872,6 +1952,14 @@ int launch_vec_inst(const MsdaParams &p, const VecPlan &plan, cudaStream_t strea
                                            dim3(kThreads), plan.stage_bytes, stream, plan.pdl, p);
       g_launch_count.fetch_add(1, std::memory_order_relaxed);
       return se != cudaSuccess ? (int)se : (int)cudaGetLastError();
+    }
+  }
+  if constexpr (P_T == 4 && SPLIT == 1) {
+    if (plan.dyn && p.sched) {
+      const cudaError_t de = launch_kernel(msda_fwd_vec<T, D, P_T, SPLIT, MATH, false, false, true>,
+                                           dim3(plan.grid, plan.grid_y, 1), dim3(kThreads), 0, stream, plan.pdl, p);
+      g_launch_count.fetch_add(1, std::memory_order_relaxed);
+      return de != cudaSuccess ? (int)de : (int)cudaGetLastError();
     }
   }
   const cudaError_t le = launch_kernel(msda_fwd_vec<T, D, P_T, SPLIT, MATH, false, false>, dim3(plan.grid, plan.grid_y, 1),
@@ -2059,6 +2147,14 @@ int forward_impl(MsdaParams p, int dtype, unsigned flags, void *workspace, size_
   if (grid < 1) grid = 1;
   plan.grid = (unsigned)grid;
   plan.grid_y = (unsigned)p.B;
+  // Dynamic unit scheduling (MSDA_B200_DYN=1): warps draw (pass, warp-slice) units from a device counter, which
+  // evens out launches whose unit count is a small non-integer multiple of the resident CTA count.
+  plan.dyn = false;
+  p.sched = nullptr;
+  if (env_int("MSDA_B200_DYN", 0) && plan.split == 1 && p.P == 4 && plan.stage_bytes == 0 && !fused && !p.chunked) {
+    p.sched = sched_slots(p.B, stream);
+    plan.dyn = p.sched != nullptr;
+  }
 
   // PDL pays when the grid fills the machine (its CTAs can only land where the previous kernel's exit) or on
   // the small-problem kernel; a partial grid placed early piles onto the first SMs that free up and runs
@@ -2143,7 +2239,7 @@ int forward_impl(MsdaParams p, int dtype, unsigned flags, void *workspace, size_
     snprintf(g_last_variant, sizeof(g_last_variant), "vec<%s,D%d,P%d,split%d>/%s%dx%d/%s/%s%s", dtype_name(dtype), p.D,
              p.P == 4 ? 4 : 0, plan.split, p.want_tiled ? "tiled" : "linear", 1 << p.tile_w_log2, 1 << p.tile_h_log2,
              p.head_major ? "head-major" : "query-major", plan.math == kFhfma ? "fhfma" : "exact",
-             fused ? "/fused-producers" : (plan.stage_bytes ? "/tma-staged" : ""));
+             fused ? "/fused-producers" : (plan.stage_bytes ? "/tma-staged" : (plan.dyn ? "/dyn" : "")));
   }
   return rc;
 }

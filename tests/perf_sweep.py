@@ -60,7 +60,7 @@ def time_calls(fns, iters, warmup=20):
 
 def set_env(cfg):
     for k in ("MSDA_B200_TILE_W", "MSDA_B200_TILE_H", "MSDA_B200_HEAD_MAJOR", "MSDA_B200_SPLIT", "MSDA_B200_CTAS_PER_SM",
-              "MSDA_B200_SMALL", "MSDA_B200_SPLIT_MAX_CTAS", "MSDA_B200_CHUNKED"):
+              "MSDA_B200_SMALL", "MSDA_B200_SPLIT_MAX_CTAS", "MSDA_B200_CHUNKED", "MSDA_B200_DYN"):
         os.environ.pop(k, None)
     for k, v in cfg.items():
         if k.startswith("MSDA_"):
@@ -120,6 +120,13 @@ def main():
         workloads = [("swinl_enc_1152x768", 1, "float16", None), ("swinl_enc_1152x768", 4, "float16", None),
                      ("swinl_enc_1152x768", 1, "float32", None), ("swinl_enc_1920x1280", 2, "float16", None),
                      ("r50_enc_608", 1, "float16", None), ("swinl_dec_1152x768", 8, "float16", None)]
+    if args.only == "dyn":
+        workloads = [("swinl_enc_1152x768", 1, "float16", None), ("swinl_enc_1152x768", 1, "float16", "adversarial"),
+                     ("swinl_enc_1152x768", 4, "float16", None), ("swinl_enc_1152x768", 1, "bfloat16", None),
+                     ("swinl_enc_1152x768", 1, "float32", None), ("swinl_enc_1920x1280", 2, "float16", None),
+                     ("r50_enc_608", 1, "float16", None), ("r50_enc_608", 2, "float16", None),
+                     ("swinl_dec_1152x768", 8, "float16", None), ("swinl_dec_1900q", 1, "float16", None),
+                     ("swinl_enc_1152x768_s4", 1, "float16", None)]
     if args.only == "decoder":
         workloads = [("swinl_dec_1152x768", 1, "float16", None), ("swinl_dec_1900q", 1, "float16", None),
                      ("swinl_dec_1152x768", 8, "float16", None), ("ref_test_mid_fp32", 1, "float32", None),
@@ -175,6 +182,13 @@ def main():
                     {"name": "small<=600ctas", "flags": 0, "MSDA_B200_SPLIT_MAX_CTAS": 600},
                     {"name": "small<=1200ctas", "flags": 0, "MSDA_B200_SPLIT_MAX_CTAS": 1200},
                     {"name": "split1", "flags": 0, "MSDA_B200_SPLIT": 1}]
+            have_ref = False
+        if args.only == "dyn":
+            cfgs = [{"name": "default", "flags": 0}, {"name": "dyn", "flags": 0, "MSDA_B200_DYN": 1},
+                    {"name": "dyn ctas_per_sm4", "flags": 0, "MSDA_B200_DYN": 1, "MSDA_B200_CTAS_PER_SM": 4},
+                    {"name": "dyn ctas_per_sm8", "flags": 0, "MSDA_B200_DYN": 1, "MSDA_B200_CTAS_PER_SM": 8},
+                    {"name": "dyn split1", "flags": 0, "MSDA_B200_DYN": 1, "MSDA_B200_SPLIT": 1},
+                    {"name": "default again", "flags": 0}]
             have_ref = False
         if args.only == "headline":
             cfgs = [c for c in cfgs if c["name"] in ("default", "exact-placeholder", "tile8x8+fhfma", "tile16x4+fhfma",
