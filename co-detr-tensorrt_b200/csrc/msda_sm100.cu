@@ -17,11 +17,13 @@
 //                     group works out the geometry of point k of the level once and broadcasts it by
 //                     shuffle; every "does not contribute" case is a weight of exactly zero, which
 //                     predicates off the load and the FMAs; fp16 multiplies in place with Blackwell's
-//                     mixed-precision FMA (PTX fma.rn.f32.f16 -> SASS FHFMA) and accumulates in fp32; the
+//                     mixed-precision FMA (PTX fma.rn.f32.f16 -> SASS FHFMA) and accumulates in fp32, the
+//                     exact paths (bf16, fp32) use the packed fp32 FMA (fma.rn.f32x2 -> FFMA2); the
 //                     grid is persistent (resident CTA count) and the next unit's first sample is loaded
 //                     while the current one is computed.  Template switches: P (4 or run-time), SPLIT
 //                     (points dealt to 2/4 lane groups), MATH (fhfma / exact), STAGE (TMA bulk-copy staging
-//                     of locations and weights, opt-in), FUSED (softmax + location arithmetic in-kernel).
+//                     of locations and weights, opt-in), FUSED (softmax + location arithmetic in-kernel), DYN
+//                     (warps draw units from a device counter, opt-in).
 //   msda_fwd_small    decoder-sized launches: 4-way point split, 128-thread CTAs, level table held in
 //                     lanes, no shared memory, no barrier.
 //   msda_pack_value + msda_fwd_packed   opt-in packed-pyramid path: 128-byte (pixel, head) entries that also
@@ -60,6 +62,9 @@ constexpr int kThreads = 256;
 #endif
 #ifndef MSDA_PIPE
 #define MSDA_PIPE 0
+#endif
+#ifndef MSDA_FFMA2
+#define MSDA_FFMA2 1  // packed fp32 FMA (FFMA2) on the exact-arithmetic paths
 #endif
 #ifndef MSDA_LB
 #define MSDA_LB 1   // levels whose row loads are issued together in the split-points path (measured: 1 is best,
@@ -346,13 +351,28 @@ __device__ __forceinline__ unsigned short ld_stream_u16(const void *ptr) {
 template <typename T, int MATH>
 struct RowFma;
 
+// Blackwell packed fp32 FMA: (a0, a1) += (x0, x1) * w in one instruction (SASS FFMA2 with the weight as a scalar
+// broadcast operand).  Each half is an ordinary round-to-nearest fmaf, so results are bit-identical to two
+// scalar FMAs; the point is one issue slot instead of two on the exact-arithmetic paths (fp32, bf16, fp16+EXACT).
+__device__ __forceinline__ void fma2(float &a0, float &a1, float x0, float x1, float w) {
+#if MSDA_FFMA2
+  unsigned long long acc, x, ww;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(acc) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(x0), "f"(x1));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(ww) : "f"(w));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(x), "l"(ww));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(acc));
+#else
+  a0 = fmaf(w, x0, a0);
+  a1 = fmaf(w, x1, a1);
+#endif
+}
+
 template <int MATH>
 struct RowFma<float, MATH> {
   static __device__ __forceinline__ void run(float (&acc)[4], const uint4 &r, float cw, unsigned /*cw16*/) {
-    acc[0] = fmaf(cw, __uint_as_float(r.x), acc[0]);
-    acc[1] = fmaf(cw, __uint_as_float(r.y), acc[1]);
-    acc[2] = fmaf(cw, __uint_as_float(r.z), acc[2]);
-    acc[3] = fmaf(cw, __uint_as_float(r.w), acc[3]);
+    fma2(acc[0], acc[1], __uint_as_float(r.x), __uint_as_float(r.y), cw);
+    fma2(acc[2], acc[3], __uint_as_float(r.z), __uint_as_float(r.w), cw);
   }
 };
 
@@ -363,8 +383,7 @@ struct RowFma<__half, kExact> {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&w[i]));
-      acc[2 * i] = fmaf(cw, f.x, acc[2 * i]);
-      acc[2 * i + 1] = fmaf(cw, f.y, acc[2 * i + 1]);
+      fma2(acc[2 * i], acc[2 * i + 1], f.x, f.y, cw);
     }
   }
 };
@@ -376,8 +395,7 @@ struct RowFma<__nv_bfloat16, kExact> {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       // bf16 -> fp32 is a 16-bit shift: keep it on the integer pipe
-      acc[2 * i] = fmaf(cw, __uint_as_float(w[i] << 16), acc[2 * i]);
-      acc[2 * i + 1] = fmaf(cw, __uint_as_float(w[i] & 0xffff0000u), acc[2 * i + 1]);
+      fma2(acc[2 * i], acc[2 * i + 1], __uint_as_float(w[i] << 16), __uint_as_float(w[i] & 0xffff0000u), cw);
     }
   }
 };

@@ -127,6 +127,12 @@ def main():
                      ("r50_enc_608", 1, "float16", None), ("r50_enc_608", 2, "float16", None),
                      ("swinl_dec_1152x768", 8, "float16", None), ("swinl_dec_1900q", 1, "float16", None),
                      ("swinl_enc_1152x768_s4", 1, "float16", None)]
+    if args.only == "exact":
+        workloads = [("swinl_enc_1152x768", 1, "bfloat16", None), ("swinl_enc_1152x768", 4, "bfloat16", None),
+                     ("swinl_enc_1152x768", 1, "float32", None), ("swinl_enc_1152x768", 1, "float16", None),
+                     ("r50_enc_608", 1, "bfloat16", None), ("swinl_dec_1152x768", 1, "bfloat16", None),
+                     ("swinl_dec_1152x768", 8, "bfloat16", None), ("swinl_enc_1920x1280", 2, "bfloat16", None),
+                     ("ref_test_mid_fp32", 1, "float32", None)]
     if args.only == "decoder":
         workloads = [("swinl_dec_1152x768", 1, "float16", None), ("swinl_dec_1900q", 1, "float16", None),
                      ("swinl_dec_1152x768", 8, "float16", None), ("ref_test_mid_fp32", 1, "float32", None),
@@ -189,6 +195,9 @@ def main():
                     {"name": "dyn ctas_per_sm8", "flags": 0, "MSDA_B200_DYN": 1, "MSDA_B200_CTAS_PER_SM": 8},
                     {"name": "dyn split1", "flags": 0, "MSDA_B200_DYN": 1, "MSDA_B200_SPLIT": 1},
                     {"name": "default again", "flags": 0}]
+            have_ref = False
+        if args.only == "exact":
+            cfgs = [{"name": "default", "flags": 0}, {"name": "exact", "flags": cb.FLAG_MATH_EXACT}]
             have_ref = False
         if args.only == "headline":
             cfgs = [c for c in cfgs if c["name"] in ("default", "exact-placeholder", "tile8x8+fhfma", "tile16x4+fhfma",

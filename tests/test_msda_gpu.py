@@ -576,6 +576,38 @@ def test_small_problem_kernel_matches_general_kernel(dt, cuda_device, monkeypatc
     assert metric(gen.float().cpu().numpy(), ref) <= gate
 
 
+@pytest.mark.parametrize("name,batch,dt", [("swinl_enc_1152x768", 1, "f16"), ("swinl_enc_1152x768", 2, "bf16"),
+                                            ("r50_enc_608", 3, "f32"), ("swinl_dec_1900q", 2, "f16")])
+def test_dynamic_unit_scheduling_is_bit_identical(name, batch, dt, cuda_device, monkeypatch):
+    """MSDA_B200_DYN=1: warps draw their (pass, warp-slice) units from a self-resetting device counter.  Which
+    warp computes a pair does not change the arithmetic of the pair, so the output must be bit-identical to the
+    strided schedule; 5,000 launches walk the 4,096-slot counter pool round more than once, and a launch under
+    stream capture must fall back to the strided schedule."""
+    monkeypatch.setenv("MSDA_B200_SPLIT", "1")
+    d = to_dev(_full_inputs(name, batch), TORCH_DT[dt], cuda_device)
+    want = cb.multi_scale_deformable_attention(*(d[k] for k in ARRAY_KEYS))
+    assert not cb.last_variant().endswith("/dyn")
+    monkeypatch.setenv("MSDA_B200_DYN", "1")
+    got = cb.multi_scale_deformable_attention(*(d[k] for k in ARRAY_KEYS))
+    assert cb.last_variant().endswith("/dyn")
+    assert torch.equal(got, want)
+    if name == "swinl_dec_1900q":
+        call = cb.PreparedForward(*(d[k] for k in ARRAY_KEYS))
+        for _ in range(5000 // batch + 1):
+            call()
+        assert torch.equal(call(), want)
+        g = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(device=cuda_device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(g, stream=side):
+                captured = call()
+                assert not cb.last_variant().endswith("/dyn")
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(captured, want)
+
+
 def test_degenerate_shapes_give_zeros(cuda_device):
     """No levels or no points: the sum is empty, the output is all zeros (and still fully written)."""
     v = torch.randn(2, 10, 8, 32, device=cuda_device, dtype=torch.float16)
