@@ -66,6 +66,10 @@ constexpr int kThreads = 256;
 #ifndef MSDA_FFMA2
 #define MSDA_FFMA2 1  // packed fp32 FMA (FFMA2) on the exact-arithmetic paths
 #endif
+#ifndef MSDA_BF16_UNPACK
+#define MSDA_BF16_UNPACK 2  // low bf16 -> fp32: 0 = compiler's shift (IMAD.U32, FMA pipe), 1 = PRMT (ALU pipe), 2 = alternate
+                            // the two (measured 60.4 / 59.5 / 59.0 us at the headline shape for 1 / 0 / 2)
+#endif
 #ifndef MSDA_LB
 #define MSDA_LB 1   // levels whose row loads are issued together in the split-points path (measured: 1 is best,
                     // more registers per thread push the 450-CTA decoder grid into a second wave)
@@ -353,7 +357,7 @@ struct RowFma;
 
 // Blackwell packed fp32 FMA: (a0, a1) += (x0, x1) * w in one instruction (SASS FFMA2 with the weight as a scalar
 // broadcast operand).  Each half is an ordinary round-to-nearest fmaf, so results are bit-identical to two
-// scalar FMAs; the point is one issue slot instead of two on the exact-arithmetic paths (fp32, bf16, fp16+EXACT).
+// scalar FMAs; the point is one issue slot instead of two on the fp32 and bf16 paths.
 __device__ __forceinline__ void fma2(float &a0, float &a1, float x0, float x1, float w) {
 #if MSDA_FFMA2
   unsigned long long acc, x, ww;
@@ -382,8 +386,10 @@ struct RowFma<__half, kExact> {
     const unsigned w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
+      // scalar FMAs here: with the HADD2.F32 unpacks on the same pipe FFMA2 measured slower (66.1 vs 62.7 us)
       const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&w[i]));
-      fma2(acc[2 * i], acc[2 * i + 1], f.x, f.y, cw);
+      acc[2 * i] = fmaf(cw, f.x, acc[2 * i]);
+      acc[2 * i + 1] = fmaf(cw, f.y, acc[2 * i + 1]);
     }
   }
 };
@@ -395,7 +401,14 @@ struct RowFma<__nv_bfloat16, kExact> {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       // bf16 -> fp32 is a 16-bit shift: keep it on the integer pipe
-      fma2(acc[2 * i], acc[2 * i + 1], __uint_as_float(w[i] << 16), __uint_as_float(w[i] & 0xffff0000u), cw);
+#if MSDA_BF16_UNPACK == 0
+      const unsigned lo = w[i] << 16;
+#else
+      unsigned lo;
+      if (MSDA_BF16_UNPACK == 1 || (i & 1)) asm("prmt.b32 %0, %1, 0, 0x1044;" : "=r"(lo) : "r"(w[i]));
+      else lo = w[i] << 16;
+#endif
+      fma2(acc[2 * i], acc[2 * i + 1], __uint_as_float(lo), __uint_as_float(w[i] & 0xffff0000u), cw);
     }
   }
 };
