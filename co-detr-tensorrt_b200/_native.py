@@ -1,6 +1,6 @@
 """Loader (and in-tree builder) of the C-ABI library ``libmsda_b200.so``.
 
-The library is compiled from ``csrc/msda_sm100.cu`` for ``sm_100a`` only and is
+The library is compiled from ``csrc/msda_sm100.cu`` and ``csrc/value_proj_sm100.cu`` for ``sm_100a`` only and is
 the *only* compute path of this package: if it cannot be loaded the package
 raises -- there is deliberately no PyTorch/CPU fallback (the reference's module
 falls back to ``multi_scale_deformable_attention_pytorch`` for CPU tensors,
@@ -21,8 +21,8 @@ CSRC_DIR = os.path.join(_PKG_DIR, "csrc")
 INCLUDE_DIR = os.path.join(_REPO_ROOT, "include")
 # MSDA_B200_LIB lets tuning experiments load an alternative build of the same sources
 LIB_PATH = os.environ.get("MSDA_B200_LIB") or os.path.join(CSRC_DIR, "libmsda_b200.so")
-SOURCES = [os.path.join(CSRC_DIR, "msda_sm100.cu")]
-HEADERS = [os.path.join(INCLUDE_DIR, "msda_b200.h")]
+SOURCES = [os.path.join(CSRC_DIR, "msda_sm100.cu"), os.path.join(CSRC_DIR, "value_proj_sm100.cu")]
+HEADERS = [os.path.join(INCLUDE_DIR, "msda_b200.h"), os.path.join(CSRC_DIR, "msda_internal.hpp")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -49,6 +49,8 @@ EXPORTED_SYMBOLS = [
     "msda_b200_algorithmic_hbm_bytes",
     "msda_b200_algorithmic_gather_bytes",
     "msda_b200_read_probe",
+    "msda_b200_value_proj_supported",
+    "msda_b200_value_proj",
 ]
 
 DTYPE_F32, DTYPE_F16, DTYPE_BF16, DTYPE_F64 = 0, 1, 2, 3
@@ -184,6 +186,10 @@ def load() -> ctypes.CDLL:
     lib.msda_b200_algorithmic_gather_bytes.argtypes = [i64, i64, i64, i64, i64, i64, ci]
     lib.msda_b200_read_probe.restype = ci
     lib.msda_b200_read_probe.argtypes = [vp, ctypes.c_size_t, ci, vp, vp]
+    lib.msda_b200_value_proj_supported.restype = ci
+    lib.msda_b200_value_proj_supported.argtypes = [i64, i64, ci]
+    lib.msda_b200_value_proj.restype = ci
+    lib.msda_b200_value_proj.argtypes = [vp, vp, vp, vp, vp, i64, i64, i64, ci, cu, vp]
     if lib.msda_b200_abi_version() != 1:
         raise NativeLibraryError("libmsda_b200.so ABI version mismatch; rebuild it")
     _lib = lib

@@ -49,6 +49,11 @@
 #include <type_traits>
 
 #include "msda_b200.h"
+#include "msda_internal.hpp"
+
+namespace msda_detail __attribute__((visibility("hidden"))) {
+std::atomic<uint64_t> launch_count{0};
+}  // namespace msda_detail
 
 namespace {
 
@@ -78,7 +83,7 @@ constexpr int kThreads = 256;
 #define MSDA_MINB_SPLIT 4
 #endif
 
-std::atomic<uint64_t> g_launch_count{0};
+std::atomic<uint64_t> &g_launch_count = msda_detail::launch_count;
 thread_local char g_last_variant[128] = "none";
 
 // ---------------------------------------------------------------------------
@@ -2290,6 +2295,8 @@ int validate_common(const void *value, const int64_t *shapes, const int64_t *sta
 }
 
 }  // namespace
+
+void msda_detail::set_last_variant(const char *text) { snprintf(g_last_variant, sizeof(g_last_variant), "%s", text); }
 
 // ---------------------------------------------------------------------------
 // C ABI

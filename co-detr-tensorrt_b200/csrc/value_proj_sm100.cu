@@ -1,0 +1,363 @@
+// SPDX-License-Identifier: Apache-2.0
+//
+// value_proj_sm100.cu -- the producer of the op's `value` input for NVIDIA B200 (sm_100a):
+//
+//     value[r, :] = key_padding_mask[r] ? 0 : x[r, :] @ W^T + bias          (r = image * S + key)
+//
+// i.e. nn.Linear + masked_fill + head split of the calling module
+// (/root/reference/codetr/multi_scale_deformable_attention.py:173-176) in ONE kernel whose output is already
+// the [B, S, M, D] tensor the sampling kernels read.  This is the one GEMM-shaped
+// neighbour of the hot path, so it runs on the 5th-generation tensor cores, hand-written:
+//
+//   * operands staged by TMA (cp.async.bulk.tensor.2d, 128-byte swizzle) into shared memory: the CTA's 128
+//     rows of x and the whole weight matrix (K, N <= 256), one mbarrier per 64-wide K chunk so the first MMAs
+//     start while the later chunks are still in flight;
+//   * one elected thread issues tcgen05.mma (cta_group::1, kind::f16, UMMA 128 x N x 16), fp32 accumulators
+//     in tensor memory (N columns x 128 lanes), completion signalled with tcgen05.commit on an mbarrier;
+//   * four epilogue warps read their lane quarter with tcgen05.ld (32x32b.x32), add the bias, zero the padded
+//     rows, round to the 16-bit element type and stage the tile in the (now free) x buffer in the same
+//     swizzled layout; one thread writes it back with TMA stores (out-of-range rows are clipped by the TMA).
+//
+// Nothing here allocates, synchronises or reads device memory on the host; the tensor maps are encoded per
+// call on the host (three cuTensorMapEncodeTiled calls, ~1 us) and passed as __grid_constant__ parameters.
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+
+#include "msda_b200.h"
+#include "msda_internal.hpp"
+
+namespace {
+
+constexpr int kTileRows = 128;    // UMMA M: one accumulator row per TMEM lane
+constexpr int kChunkK = 64;       // 16-bit elements per 128-byte swizzle row
+constexpr int kUmmaK = 16;        // K of one tcgen05.mma for 16-bit inputs
+constexpr int kMaxChunks = 4;     // K <= 256
+constexpr int kMaxN = 256;
+constexpr int kEpilogueWarps = 4;
+constexpr int kThreads = (kEpilogueWarps + 1) * 32;  // + one producer / MMA warp
+
+struct ProjParams {
+  const void *bias;            // [N] in the element type, or nullptr
+  const unsigned char *mask;   // [rows], non-zero = padded key (row of zeros), or nullptr
+  int rows, K, N;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// Spin on the barrier's phase; a transfer that never completes (a bad tensor map) traps instead of hanging
+// the GPU until the watchdog.
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+  unsigned done = 0;
+  for (unsigned spins = 0; !done; ++spins) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (spins > (1u << 26)) __trap();
+  }
+}
+
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                   smem_u32(dst)),
+               "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, const void *src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(smem_u32(src)),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
+
+// Shared-memory matrix descriptor of a K-major tile whose rows are 128 bytes, 128-byte swizzled (what the
+// TMA wrote): start address >> 4 in bits [0,14), stride between 8-row groups (1024 B) >> 4 in bits [32,46),
+// descriptor version 1 in bits [46,48), layout type 2 (SWIZZLE_128B) in bits [61,64).
+__device__ __forceinline__ uint64_t umma_desc_k_major_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3ffffu) >> 4) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// D[tmem] (+)= A[smem] * B[smem]^T, issued by one thread for the whole CTA
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// 32 consecutive accumulator columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_load_32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+template <bool BF16>
+__device__ __forceinline__ float elem_to_float(unsigned short bits) {
+  if constexpr (BF16) return __uint_as_float((unsigned)bits << 16);
+  else return __half2float(__ushort_as_half(bits));
+}
+template <bool BF16>
+__device__ __forceinline__ unsigned pack_pair(float a, float b) {
+  if constexpr (BF16) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const unsigned *>(&h);
+  } else {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const unsigned *>(&h);
+  }
+}
+
+// Dynamic shared memory (1024-byte aligned, the swizzle atom):
+//   [0, tile_bytes)        x tile: K/64 chunks of 128 rows x 128 B; reused as the output staging tile
+//                          (N/64 chunks of 128 rows x 128 B), tile_bytes = 16 KB * max(K, N) / 64
+//   [.., + K/64 * N*128)   weight: K/64 chunks of N rows x 128 B
+//   bias as fp32 [N], then the barriers and the TMEM base address
+template <bool BF16>
+__global__ void __launch_bounds__(kThreads, 1)
+value_proj_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                  const __grid_constant__ CUtensorMap map_out, const ProjParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  // the swizzle atom needs 1024-byte alignment; the launch asks for 1 KB of slack to round up into
+  unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int chunks = p.K / kChunkK;
+  const int out_chunks = p.N / kChunkK;
+  const int tile_bytes = kTileRows * 128 * max(chunks, out_chunks);
+  unsigned char *x_tile = smem;
+  unsigned char *w_tile = smem + tile_bytes;
+  float *bias_f = reinterpret_cast<float *>(w_tile + (size_t)chunks * p.N * 128);
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(bias_f + kMaxN);  // [kMaxChunks]
+  uint64_t *done_bar = full_bar + kMaxChunks;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(done_bar + 1);
+
+  const int warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31);
+  const int row0 = (int)blockIdx.x * kTileRows;
+  const uint32_t tmem_cols = p.N <= 32 ? 32u : p.N <= 64 ? 64u : p.N <= 128 ? 128u : 256u;
+
+  // ---- set-up: barriers + TMEM allocation (producer warp), bias to fp32 (epilogue warps) ----
+  if (warp == kEpilogueWarps) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_out) : "memory");
+      for (int c = 0; c < chunks; ++c) mbar_init(&full_bar[c], 1);
+      mbar_init(done_bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  } else {
+    for (int n = (int)threadIdx.x; n < p.N; n += kEpilogueWarps * 32) {
+      bias_f[n] = p.bias ? elem_to_float<BF16>(static_cast<const unsigned short *>(p.bias)[n]) : 0.f;
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == kEpilogueWarps) {
+    // ---- producer + MMA issuer: one thread ----
+    if (lane == 0) {
+      const unsigned chunk_bytes = (unsigned)(kTileRows * 128 + p.N * 128);
+      for (int c = 0; c < chunks; ++c) {
+        mbar_expect_tx(&full_bar[c], chunk_bytes);
+        tma_load_2d(x_tile + (size_t)c * kTileRows * 128, &map_x, c * kChunkK, row0, &full_bar[c]);
+        tma_load_2d(w_tile + (size_t)c * p.N * 128, &map_w, c * kChunkK, 0, &full_bar[c]);
+      }
+      // instruction descriptor: D = fp32 (bits 4-5 = 1), A / B format (bits 7-9 / 10-12: 0 = f16, 1 = bf16),
+      // both operands K-major (bits 15, 16 = 0), N >> 3 in bits 17-22, M >> 4 in bits 24-28
+      const uint32_t fmt = BF16 ? 1u : 0u;
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.N >> 3) << 17) | ((uint32_t)(kTileRows >> 4) << 24);
+      for (int c = 0; c < chunks; ++c) {
+        mbar_wait(&full_bar[c], 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_addr = smem_u32(x_tile + (size_t)c * kTileRows * 128);
+        const uint32_t b_addr = smem_u32(w_tile + (size_t)c * p.N * 128);
+#pragma unroll
+        for (int k = 0; k < kChunkK / kUmmaK; ++k) {
+          // inside the 128-byte swizzle row a K step of 16 elements is 32 bytes of start address
+          umma_f16(tmem_base, umma_desc_k_major_sw128(a_addr + k * kUmmaK * 2), umma_desc_k_major_sw128(b_addr + k * kUmmaK * 2),
+                   idesc, (c | k) != 0 ? 1u : 0u);
+        }
+      }
+      umma_commit(done_bar);  // arrives when every MMA above has written TMEM (and read its operands)
+    }
+    __syncwarp();
+  } else {
+    // ---- epilogue: TMEM -> registers -> (+bias, mask, round) -> swizzled staging tile ----
+    mbar_wait(done_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int rl = warp * 32 + lane;  // row inside the tile = TMEM lane
+    const int r = row0 + rl;
+    const bool padded = p.mask != nullptr && r < p.rows && p.mask[r] != 0;
+    unsigned char *stage = x_tile;
+    for (int c32 = 0; c32 < p.N / 32; ++c32) {
+      uint32_t v[32];
+      tmem_load_32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c32 * 32), v);
+      unsigned char *row_base = stage + (size_t)(c32 >> 1) * kTileRows * 128 + (size_t)rl * 128;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {  // four 16-byte pieces = 8 elements each
+        uint4 o;
+        unsigned *ow = reinterpret_cast<unsigned *>(&o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int col = c32 * 32 + i * 8 + j * 2;
+          const float a = padded ? 0.f : __uint_as_float(v[i * 8 + j * 2]) + bias_f[col];
+          const float b = padded ? 0.f : __uint_as_float(v[i * 8 + j * 2 + 1]) + bias_f[col + 1];
+          ow[j] = pack_pair<BF16>(a, b);
+        }
+        const int piece = (c32 & 1) * 4 + i;
+        *reinterpret_cast<uint4 *>(row_base + ((piece ^ (rl & 7)) << 4)) = o;
+      }
+    }
+    // make the generic-proxy writes visible to the TMA (async proxy), then one thread stores the tile
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(kEpilogueWarps * 32) : "memory");
+    if (threadIdx.x == 0) {
+      for (int c = 0; c < out_chunks; ++c) tma_store_2d(&map_out, stage + (size_t)c * kTileRows * 128, c * kChunkK, row0);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem must outlive the reads
+    }
+  }
+
+  // ---- teardown: everyone is done with TMEM, the allocating warp frees it ----
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == kEpilogueWarps) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+  static std::atomic<void *> cached{nullptr};
+  void *fn = cached.load(std::memory_order_acquire);
+  if (!fn) {
+    cudaDriverEntryPointQueryResult status;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &status) != cudaSuccess ||
+        status != cudaDriverEntryPointSuccess) {
+      return nullptr;
+    }
+    cached.store(fn, std::memory_order_release);
+  }
+  return reinterpret_cast<EncodeTiledFn>(fn);
+}
+
+// [outer, inner] row-major 16-bit matrix, box = 64 x box_outer elements, 128-byte swizzle
+bool make_map(CUtensorMap *map, const void *base, bool bf16, uint64_t inner, uint64_t outer, uint32_t box_outer) {
+  EncodeTiledFn encode = encode_tiled_fn();
+  if (!encode) return false;
+  const cuuint64_t dims[2] = {inner, outer};
+  const cuuint64_t strides[1] = {inner * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)kChunkK, box_outer};
+  const cuuint32_t elem_strides[2] = {1, 1};
+  return encode(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(base), dims,
+                strides, box, elem_strides, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+size_t proj_smem_bytes(int K, int N) {
+  const int chunks = K / kChunkK, out_chunks = N / kChunkK;
+  const size_t tile = (size_t)kTileRows * 128 * (chunks > out_chunks ? chunks : out_chunks);
+  return tile + (size_t)chunks * N * 128 + kMaxN * sizeof(float) + (kMaxChunks + 1) * sizeof(uint64_t) + 16;
+}
+
+}  // namespace
+
+extern "C" {
+
+int msda_b200_value_proj_supported(int64_t in_features, int64_t out_features, int dtype) {
+  return (dtype == MSDA_F16 || dtype == MSDA_BF16) && in_features >= kChunkK && in_features <= kMaxChunks * kChunkK &&
+                 in_features % kChunkK == 0 && out_features >= kChunkK && out_features <= kMaxN && out_features % kChunkK == 0
+             ? 1
+             : 0;
+}
+
+int msda_b200_value_proj(const void *x, const void *weight, const void *bias, const unsigned char *key_padding_mask, void *value,
+                         int64_t rows, int64_t in_features, int64_t out_features, int dtype, unsigned flags, void *stream_) {
+  (void)flags;
+  if (rows < 0 || in_features <= 0 || out_features <= 0) return MSDA_ERR_BAD_SHAPE;
+  if (dtype != MSDA_F16 && dtype != MSDA_BF16 && dtype != MSDA_F32 && dtype != MSDA_F64) return MSDA_ERR_BAD_DTYPE;
+  if (!msda_b200_value_proj_supported(in_features, out_features, dtype)) return MSDA_ERR_UNSUPPORTED;
+  if (rows == 0) return MSDA_OK;
+  if (rows > (int64_t)INT32_MAX - kTileRows) return MSDA_ERR_BAD_SHAPE;
+  if (!x || !weight || !value) return MSDA_ERR_NULL_POINTER;
+  if (((uintptr_t)x | (uintptr_t)weight | (uintptr_t)value) & 15u) return MSDA_ERR_UNSUPPORTED;  // TMA base alignment
+  if (bias && ((uintptr_t)bias & 1u)) return MSDA_ERR_UNSUPPORTED;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const bool bf16 = dtype == MSDA_BF16;
+  const int K = (int)in_features, N = (int)out_features;
+
+  CUtensorMap map_x, map_w, map_out;
+  if (!make_map(&map_x, x, bf16, (uint64_t)K, (uint64_t)rows, kTileRows) || !make_map(&map_w, weight, bf16, (uint64_t)K, (uint64_t)N, (uint32_t)N) ||
+      !make_map(&map_out, value, bf16, (uint64_t)N, (uint64_t)rows, kTileRows)) {
+    return MSDA_ERR_UNSUPPORTED;
+  }
+  ProjParams p;
+  p.bias = bias;
+  p.mask = key_padding_mask;
+  p.rows = (int)rows;
+  p.K = K;
+  p.N = N;
+  const size_t smem = proj_smem_bytes(K, N) + 1024;  // + slack for the 1024-byte round-up in the kernel
+  auto kernel = bf16 ? value_proj_kernel<true> : value_proj_kernel<false>;
+  // opt in to > 48 KB of dynamic shared memory once per (device, instantiation)
+  static std::atomic<int> attr_set[64][2];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return MSDA_ERR_UNSUPPORTED;
+  if (!attr_set[dev][bf16].load(std::memory_order_acquire)) {
+    const cudaError_t ae = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)(proj_smem_bytes(kMaxChunks * kChunkK, kMaxN) + 1024));
+    if (ae != cudaSuccess) return (int)ae;
+    attr_set[dev][bf16].store(1, std::memory_order_release);
+  }
+  const unsigned grid = (unsigned)((rows + kTileRows - 1) / kTileRows);
+  kernel<<<grid, kThreads, smem, stream>>>(map_x, map_w, map_out, p);
+  msda_detail::launch_count.fetch_add(1, std::memory_order_relaxed);
+  msda_detail::set_last_variant(bf16 ? "value_proj<bf16>/tcgen05" : "value_proj<f16>/tcgen05");
+  return (int)cudaGetLastError();
+}
+
+}  // extern "C"

@@ -7,7 +7,8 @@ the op can be exercised in its calling context here (same constructor arguments,
 ``sampling_offsets``, ``attention_weights``, ``value_proj``, ``output_proj`` -- so a reference ``state_dict``
 loads, same forward signature and shape conventions); (2) ``fused_producers=True`` routes the softmax and the
 sampling-location arithmetic (:180-200) into the kernel through ``msda_b200_forward_fused`` instead of running
-them as separate PyTorch ops.
+them as separate PyTorch ops, and ``fused_value_proj=True`` replaces ``value_proj`` +
+``masked_fill`` (:173-176) by the tensor-core kernel ``msda_b200_value_proj`` (section 8(f).4).
 
 Differences, both deliberate: CPU tensors raise (the reference falls back to
 ``multi_scale_deformable_attention_pytorch`` at :207-210; this package has no CPU path), and ``norm_cfg`` /
@@ -27,11 +28,12 @@ from . import ops
 
 class MultiScaleDeformableAttention(nn.Module):
     """Constructor arguments, parameter names and the forward contract are the reference's (see the module
-    docstring); ``fused_producers`` is the only addition."""
+    docstring); ``fused_producers`` and ``fused_value_proj`` are the only additions."""
 
     def __init__(self, embed_dims: int = 256, num_heads: int = 8, num_levels: int = 4, num_points: int = 4,
                  im2col_step: int = 64, dropout: float = 0.1, batch_first: bool = False, norm_cfg: Optional[dict] = None,
-                 init_cfg: Optional[dict] = None, value_proj_ratio: float = 1.0, fused_producers: bool = False):
+                 init_cfg: Optional[dict] = None, value_proj_ratio: float = 1.0, fused_producers: bool = False,
+                 fused_value_proj: bool = False):
         super().__init__()
         per_head, rem = divmod(embed_dims, num_heads)
         if rem:  # reference :56-57
@@ -40,7 +42,7 @@ class MultiScaleDeformableAttention(nn.Module):
             warnings.warn(f"{per_head} channels per head is not a power of two: the op falls back to its generic kernel")
         for name, val in dict(embed_dims=embed_dims, num_heads=num_heads, num_levels=num_levels, num_points=num_points,
                               im2col_step=im2col_step, batch_first=batch_first, norm_cfg=norm_cfg,
-                              fused_producers=fused_producers).items():
+                              fused_producers=fused_producers, fused_value_proj=fused_value_proj).items():
             setattr(self, name, val)
         samples = num_heads * num_levels * num_points
         inner = int(embed_dims * value_proj_ratio)
@@ -74,7 +76,13 @@ class MultiScaleDeformableAttention(nn.Module):
     # -- pieces of the forward -----------------------------------------------------------------------
     def _keys(self, value: torch.Tensor, key_padding_mask: Optional[torch.Tensor]) -> torch.Tensor:
         """value_proj, zero the padded keys, split heads (reference :173-176) -> [bs, S, M, D]."""
-        v = self.value_proj(value)
+        lin = self.value_proj
+        if (self.fused_value_proj and not torch.is_grad_enabled()
+                and ops.value_proj_supported(lin.in_features, lin.out_features, value.dtype)):
+            # Linear + masked_fill + head split in one tcgen05 kernel (SURVEY.md section 8(f).4)
+            mask = None if key_padding_mask is None else key_padding_mask.to(torch.bool).contiguous()
+            return ops.value_proj(value.contiguous(), lin.weight, lin.bias, mask, num_heads=self.num_heads)
+        v = lin(value)
         if key_padding_mask is not None:
             v = v.masked_fill(key_padding_mask.unsqueeze(-1), 0.0)
         return v.unflatten(-1, (self.num_heads, -1))

@@ -293,6 +293,42 @@ def forward_fused(
     return out
 
 
+def value_proj_supported(in_features: int, out_features: int, dtype: torch.dtype) -> bool:
+    """Whether :func:`value_proj` has a tensor-core kernel for this Linear (16-bit dtype, both widths multiples
+    of 64 and at most 256)."""
+    return dtype in _DTYPES and bool(_lib.msda_b200_value_proj_supported(int(in_features), int(out_features), _DTYPES[dtype]))
+
+
+def value_proj(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None, key_padding_mask: Optional[Tensor] = None,
+               num_heads: Optional[int] = None) -> Tensor:
+    """Producer of the op's ``value`` input in one tcgen05 kernel: ``masked_fill(linear(x, weight, bias),
+    key_padding_mask[..., None], 0)`` (/root/reference/codetr/multi_scale_deformable_attention.py:173-176).
+
+    ``x [bs, S, in]``, ``weight [out, in]``, ``bias [out]`` or None, ``key_padding_mask [bs, S]`` bool or None.
+    Returns ``[bs, S, out]``, or ``[bs, S, num_heads, out // num_heads]`` when ``num_heads`` is given (a view:
+    the kernel's output already is the op's ``[bs, S, M, D]`` layout).  Raises for shapes / dtypes without a
+    kernel (see :func:`value_proj_supported`); there is no fallback inside this function."""
+    _require(x.is_cuda and weight.is_cuda and x.device == weight.device, "value_proj needs CUDA tensors on one device")
+    _require(x.dim() == 3 and weight.dim() == 2 and weight.shape[1] == x.shape[-1], "bad x / weight shapes")
+    _require(x.is_contiguous() and weight.is_contiguous(), "x and weight have to be contiguous")
+    _require(x.dtype == weight.dtype, "x and weight dtypes differ")
+    bs, keys, fin = x.shape
+    fout = weight.shape[0]
+    _require(value_proj_supported(fin, fout, x.dtype), f"no value_proj kernel for {fin} -> {fout} in {x.dtype}")
+    if bias is not None:
+        _require(bias.is_cuda and bias.is_contiguous() and bias.dtype == x.dtype and tuple(bias.shape) == (fout,), "bad bias")
+    if key_padding_mask is not None:
+        _require(key_padding_mask.is_cuda and key_padding_mask.dtype == torch.bool and key_padding_mask.is_contiguous()
+                 and tuple(key_padding_mask.shape) == (bs, keys), "key_padding_mask must be a contiguous bool [bs, S] CUDA tensor")
+    out = torch.empty((bs, keys, fout), dtype=x.dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = _lib.msda_b200_value_proj(x.data_ptr(), weight.data_ptr(), 0 if bias is None else bias.data_ptr(),
+                                       0 if key_padding_mask is None else key_padding_mask.data_ptr(), out.data_ptr(),
+                                       bs * keys, fin, fout, _DTYPES[x.dtype], 0, _stream_ptr(x.device, None))
+    _check(rc)
+    return out if num_heads is None else out.view(bs, keys, num_heads, fout // num_heads)
+
+
 def plugin_enqueue(
     value_dims: Sequence[int],
     loc_dims: Sequence[int],

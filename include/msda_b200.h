@@ -222,6 +222,24 @@ uint64_t msda_b200_algorithmic_gather_bytes(int64_t batch, int64_t num_heads, in
                                             int64_t num_levels, int64_t num_queries, int64_t num_points,
                                             int dtype);
 
+/* Producer of the `value` input: nn.Linear + masked_fill + head split of the
+ * calling module (/root/reference/codetr/multi_scale_deformable_attention.py:173-176) in one tensor-core
+ * kernel (TMA-staged operands, tcgen05.mma into tensor memory, bias / mask / rounding in the epilogue):
+ *
+ *     value[r, :] = key_padding_mask[r] ? 0 : x[r, :] @ weight^T + bias,        r in [0, rows = B*S)
+ *
+ * x [rows, in_features], weight [out_features, in_features] (nn.Linear layout), bias [out_features] or NULL,
+ * key_padding_mask [rows] bytes (non-zero = padded key, torch.bool layout) or NULL, value [rows, out_features]
+ * = the [B, S, M, D] tensor msda_b200_forward reads.  x / weight / bias / value share `dtype` (MSDA_F16 or
+ * MSDA_BF16), are contiguous and 16-byte aligned.  Supported: in_features and out_features multiples of 64,
+ * at most 256 (msda_b200_value_proj_supported says so without a GPU); anything else returns
+ * MSDA_ERR_UNSUPPORTED and the caller keeps its own GEMM.  Same conventions as the other entry points: no
+ * allocation, no synchronisation, launches only on `stream`, capture-safe. */
+int msda_b200_value_proj_supported(int64_t in_features, int64_t out_features, int dtype);
+int msda_b200_value_proj(const void *x, const void *weight, const void *bias, const unsigned char *key_padding_mask,
+                         void *value, int64_t rows, int64_t in_features, int64_t out_features, int dtype, unsigned flags,
+                         void *stream);
+
 /* Read-bandwidth probe used for the roofline denominators that
  * MEASURED_PEAKS.json does not carry (L2): every thread block streams
  * `bytes` of `buf` (16-byte loads) `repeats` times; a working set below the

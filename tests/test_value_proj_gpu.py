@@ -1,0 +1,126 @@
+"""The tensor-core producer of the op's ``value`` input (``msda_b200_value_proj``: Linear + masked_fill + head
+split, reference multi_scale_deformable_attention.py:173-176) against plain PyTorch in fp32 on the same 16-bit
+inputs.  Gate: one rounding of the 16-bit output (2^-11 relative for fp16, 2^-8 for bf16) plus one more unit
+for accumulation-order effects at a rounding boundary; masked rows are exactly zero."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+import codetr_b200 as cb
+
+pytestmark = pytest.mark.gpu
+
+ULP = {torch.float16: 2.0 ** -11, torch.bfloat16: 2.0 ** -8}
+
+
+def _case(device, dtype, bs, keys, fin, fout, bias=True, mask=True, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x = torch.randn(bs, keys, fin, generator=g).to(device=device, dtype=dtype)
+    w = (torch.randn(fout, fin, generator=g) / fin ** 0.5).to(device=device, dtype=dtype)
+    b = torch.randn(fout, generator=g).to(device=device, dtype=dtype) if bias else None
+    m = None
+    if mask:
+        m = torch.rand(bs, keys, generator=g).to(device) < 0.2
+        m[:, -1] = True
+    return x, w, b, m
+
+
+def _reference(x, w, b, m):
+    ref = F.linear(x.float(), w.float(), None if b is None else b.float())
+    return ref if m is None else ref.masked_fill(m[..., None], 0.0)
+
+
+def _check(out, ref, dtype, m):
+    assert out.dtype == dtype and out.shape == ref.shape
+    err = (out.float() - ref).abs()
+    bound = 2.0 * ULP[dtype] * ref.abs() + 1e-5  # + fp32 accumulation noise of a K=256 dot product
+    worst = float((err - bound).max())
+    assert worst <= 0.0, f"exceeds two output roundings by {worst:.3e}"
+    if m is not None:
+        assert torch.count_nonzero(out[m]) == 0
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("bs,keys", [(1, 1), (1, 127), (1, 128), (2, 129), (3, 1000), (1, 18414)])
+def test_value_proj_matches_linear_masked_fill(bs, keys, dtype, cuda_device):
+    x, w, b, m = _case(cuda_device, dtype, bs, keys, 256, 256)
+    out = cb.value_proj(x, w, b, m)
+    torch.cuda.synchronize()
+    assert cb.last_variant().startswith("value_proj<") and "tcgen05" in cb.last_variant()
+    _check(out, _reference(x, w, b, m), dtype, m)
+    # and within the same bound of what the module would have computed with cuBLAS in 16 bits
+    lib = F.linear(x, w, b).masked_fill(m[..., None], 0.0)
+    assert float((out.float() - lib.float()).abs().max()) <= float(4.0 * ULP[dtype] * lib.float().abs().max() + 1e-6)
+
+
+@pytest.mark.parametrize("fin,fout", [(64, 64), (128, 256), (256, 128), (192, 64), (64, 192)])
+@pytest.mark.parametrize("bias,mask", [(True, False), (False, True), (False, False)])
+def test_value_proj_shapes_and_optional_inputs(fin, fout, bias, mask, cuda_device):
+    for dtype in (torch.float16, torch.bfloat16):
+        x, w, b, m = _case(cuda_device, dtype, 2, 333, fin, fout, bias=bias, mask=mask, seed=fin + fout)
+        out = cb.value_proj(x, w, b, m)
+        torch.cuda.synchronize()
+        _check(out, _reference(x, w, b, m), dtype, m)
+
+
+def test_value_proj_output_is_the_ops_value_layout(cuda_device):
+    x, w, b, m = _case(cuda_device, torch.float16, 2, 200, 256, 256)
+    v = cb.value_proj(x, w, b, m, num_heads=8)
+    assert tuple(v.shape) == (2, 200, 8, 32) and v.is_contiguous()
+    flat = cb.value_proj(x, w, b, m)
+    assert torch.equal(v.view(2, 200, 256), flat)  # deterministic, and the head split is a pure view
+
+
+def test_value_proj_rejects_what_it_has_no_kernel_for(cuda_device):
+    assert not cb.value_proj_supported(256, 256, torch.float32)
+    assert not cb.value_proj_supported(320, 256, torch.float16) and not cb.value_proj_supported(256, 96, torch.float16)
+    x, w, b, m = _case(cuda_device, torch.float16, 1, 10, 256, 256)
+    with pytest.raises(RuntimeError):
+        cb.value_proj(x.float(), w.float(), b.float(), m)
+    with pytest.raises(RuntimeError):
+        cb.value_proj(x.transpose(0, 1), w, b, m)
+    with pytest.raises(RuntimeError):
+        cb.value_proj(x, w, b, m.to(torch.uint8))
+    empty = cb.value_proj(x[:, :0].contiguous(), w, b, None)
+    assert tuple(empty.shape) == (1, 0, 256)
+
+
+def test_value_proj_under_cuda_graph_and_side_stream(cuda_device):
+    x, w, b, m = _case(cuda_device, torch.bfloat16, 2, 500, 256, 256)
+    want = cb.value_proj(x, w, b, m)
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream(device=cuda_device)
+    side.wait_stream(torch.cuda.current_stream())
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g, stream=side):
+            got = cb.value_proj(x, w, b, m)
+    got.zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_module_with_fused_value_proj(dtype, cuda_device):
+    """``fused_value_proj=True`` swaps the module's Linear + masked_fill for the kernel; the layer output must
+    agree with the unfused layer to 16-bit rounding."""
+    from test_module import _inputs
+
+    torch.manual_seed(0)
+    mod = cb.MultiScaleDeformableAttention(embed_dims=256, num_heads=8, num_levels=5, num_points=4, dropout=0.0).to(cuda_device, dtype)
+    with torch.no_grad():
+        mod.attention_weights.weight.normal_(0, 0.05)
+        mod.sampling_offsets.weight.normal_(0, 0.02)
+        mod.value_proj.bias.normal_(0, 0.1)
+    mod.eval()
+    query, value, ref, shapes, lsi, mask = _inputs(cuda_device, dtype, None)
+    kw = dict(value=value, key_padding_mask=mask, reference_points=ref, spatial_shapes=shapes, level_start_index=lsi)
+    with torch.no_grad():
+        a = mod(query, **kw)
+        launches = cb.launch_count()
+        mod.fused_value_proj = True
+        b = mod(query, **kw)
+        assert cb.launch_count() == launches + 2  # value_proj + the sampling kernel
+    err = float((a.float() - b.float()).abs().max() / a.float().abs().max())
+    assert err < (4e-3 if dtype == torch.float16 else 2e-2), err
