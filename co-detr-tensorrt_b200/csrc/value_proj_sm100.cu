@@ -29,6 +29,7 @@
 #include <atomic>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "msda_b200.h"
@@ -265,6 +266,190 @@ value_proj_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
 }
 
 // ---------------------------------------------------------------------------
+// Persistent, warp-specialised variant (the default).  One CTA per SM loops over row tiles:
+//   warp 4  TMA producer: the weight matrix once (resident for the CTA's lifetime), then the x tiles as a ring
+//           of 64-wide K chunks (kStages x 16 KB), running ahead of the MMAs by up to kStages chunks;
+//   warp 5  MMA issuer: tcgen05.mma into one of TWO accumulator buffers in tensor memory, tcgen05.commit frees
+//           each ring slot and publishes each finished accumulator;
+//   warps 0-3  epilogue: tcgen05.ld of their lane quarter, bias / mask / rounding, 32-byte stores straight to
+//           global memory (each thread owns one output row) -- so the epilogue of tile i overlaps the loads and
+//           MMAs of tile i+1, and no shared memory is spent on an output staging tile.
+// ---------------------------------------------------------------------------
+constexpr int kStages = 5;
+constexpr int kPersistentThreads = (kEpilogueWarps + 2) * 32;
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void store_32B(void *dst, const unsigned (&w)[8], bool wide) {
+  if (wide) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
+                 "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+                 : "memory");
+  } else {
+    reinterpret_cast<uint4 *>(dst)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    reinterpret_cast<uint4 *>(dst)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+  }
+}
+
+// Dynamic shared memory (1024-byte aligned): weight chunks (K/64 x N x 128 B), x ring (kStages x 16 KB),
+// bias as fp32 [N], barriers, TMEM base address.
+template <bool BF16>
+__global__ void __launch_bounds__(kPersistentThreads, 1)
+value_proj_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const ProjParams p,
+                             unsigned char *__restrict__ out, int wide_stores) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int chunks = p.K / kChunkK;
+  unsigned char *w_tile = smem;
+  unsigned char *ring = smem + (size_t)chunks * p.N * 128;
+  float *bias_f = reinterpret_cast<float *>(ring + (size_t)kStages * kTileRows * 128);
+  uint64_t *w_full = reinterpret_cast<uint64_t *>(bias_f + kMaxN);
+  uint64_t *a_full = w_full + 1;            // [kStages]
+  uint64_t *a_empty = a_full + kStages;     // [kStages]
+  uint64_t *acc_full = a_empty + kStages;   // [2]
+  uint64_t *acc_empty = acc_full + 2;       // [2]
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+
+  const int warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31);
+  const int tiles = (p.rows + kTileRows - 1) / kTileRows;
+  const uint32_t acc_cols = p.N <= 32 ? 32u : p.N <= 64 ? 64u : p.N <= 128 ? 128u : 256u;  // per accumulator buffer
+  const uint32_t tmem_cols = 2 * acc_cols;
+
+  if (warp == kEpilogueWarps) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+      mbar_init(w_full, 1);
+      for (int s = 0; s < kStages; ++s) {
+        mbar_init(&a_full[s], 1);
+        mbar_init(&a_empty[s], 1);
+      }
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(&acc_full[b], 1);
+        mbar_init(&acc_empty[b], kEpilogueWarps);
+      }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+  } else if (warp == kEpilogueWarps + 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  } else {
+    for (int n = (int)threadIdx.x; n < p.N; n += kEpilogueWarps * 32) {
+      bias_f[n] = p.bias ? elem_to_float<BF16>(static_cast<const unsigned short *>(p.bias)[n]) : 0.f;
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == kEpilogueWarps) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      mbar_expect_tx(w_full, (unsigned)(chunks * p.N * 128));
+      for (int c = 0; c < chunks; ++c) tma_load_2d(w_tile + (size_t)c * p.N * 128, &map_w, c * kChunkK, 0, w_full);
+      int stage = 0;
+      unsigned phase = 0;
+      for (int tile = (int)blockIdx.x; tile < tiles; tile += (int)gridDim.x) {
+        for (int c = 0; c < chunks; ++c) {
+          mbar_wait(&a_empty[stage], phase ^ 1u);  // a fresh barrier passes the wait on the opposite parity
+          mbar_expect_tx(&a_full[stage], (unsigned)(kTileRows * 128));
+          tma_load_2d(ring + (size_t)stage * kTileRows * 128, &map_x, c * kChunkK, tile * kTileRows, &a_full[stage]);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == kEpilogueWarps + 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t fmt = BF16 ? 1u : 0u;
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.N >> 3) << 17) | ((uint32_t)(kTileRows >> 4) << 24);
+      mbar_wait(w_full, 0);
+      int stage = 0;
+      unsigned phase = 0;
+      int t = 0;
+      for (int tile = (int)blockIdx.x; tile < tiles; tile += (int)gridDim.x, ++t) {
+        const int buf = t & 1;
+        mbar_wait(&acc_empty[buf], (((unsigned)t >> 1) & 1u) ^ 1u);  // the epilogue has drained this accumulator
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t acc = tmem_base + (uint32_t)buf * acc_cols;
+        for (int c = 0; c < chunks; ++c) {
+          mbar_wait(&a_full[stage], phase);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a_addr = smem_u32(ring + (size_t)stage * kTileRows * 128);
+          const uint32_t b_addr = smem_u32(w_tile + (size_t)c * p.N * 128);
+#pragma unroll
+          for (int k = 0; k < kChunkK / kUmmaK; ++k) {
+            umma_f16(acc, umma_desc_k_major_sw128(a_addr + k * kUmmaK * 2), umma_desc_k_major_sw128(b_addr + k * kUmmaK * 2), idesc,
+                     (c | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&a_empty[stage]);  // the slot is free once these MMAs have read it
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(&acc_full[buf]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===== epilogue =====
+    const int rl = warp * 32 + lane;
+    const size_t row_bytes = (size_t)p.N * 2;
+    int t = 0;
+    for (int tile = (int)blockIdx.x; tile < tiles; tile += (int)gridDim.x, ++t) {
+      const int buf = t & 1;
+      const int r = tile * kTileRows + rl;
+      const bool in_range = r < p.rows;
+      const bool padded = p.mask != nullptr && in_range && p.mask[r] != 0;
+      mbar_wait(&acc_full[buf], ((unsigned)t >> 1) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t acc = tmem_base + (uint32_t)buf * acc_cols + ((uint32_t)(warp * 32) << 16);
+      unsigned char *orow = out + (size_t)r * row_bytes;
+      for (int c32 = 0; c32 < p.N / 32; ++c32) {
+        uint32_t v[32];
+        tmem_load_32(acc + (uint32_t)(c32 * 32), v);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {  // two 32-byte pieces = 16 elements each
+          unsigned ow[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int col = c32 * 32 + i * 16 + j * 2;
+            const float a = padded ? 0.f : __uint_as_float(v[i * 16 + j * 2]) + bias_f[col];
+            const float b = padded ? 0.f : __uint_as_float(v[i * 16 + j * 2 + 1]) + bias_f[col + 1];
+            ow[j] = pack_pair<BF16>(a, b);
+          }
+          if (in_range) store_32B(orow + (size_t)c32 * 64 + i * 32, ow, wide_stores != 0);
+        }
+      }
+      // this warp has read its quarter of the accumulator: hand the buffer back to the MMA issuer
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == kEpilogueWarps + 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+size_t persistent_smem_bytes(int K, int N) {
+  return (size_t)(K / kChunkK) * N * 128 + (size_t)kStages * kTileRows * 128 + kMaxN * sizeof(float) +
+         (1 + 2 * kStages + 4) * sizeof(uint64_t) + 16;
+}
+
+// ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -330,9 +515,11 @@ int msda_b200_value_proj(const void *x, const void *weight, const void *bias, co
   const bool bf16 = dtype == MSDA_BF16;
   const int K = (int)in_features, N = (int)out_features;
 
+  const char *single = getenv("MSDA_B200_VPROJ_SINGLE_TILE");
+  const bool single_tile = single && *single == '1';
   CUtensorMap map_x, map_w, map_out;
   if (!make_map(&map_x, x, bf16, (uint64_t)K, (uint64_t)rows, kTileRows) || !make_map(&map_w, weight, bf16, (uint64_t)K, (uint64_t)N, (uint32_t)N) ||
-      !make_map(&map_out, value, bf16, (uint64_t)N, (uint64_t)rows, kTileRows)) {
+      (single_tile && !make_map(&map_out, value, bf16, (uint64_t)N, (uint64_t)rows, kTileRows))) {
     return MSDA_ERR_UNSUPPORTED;
   }
   ProjParams p;
@@ -341,22 +528,42 @@ int msda_b200_value_proj(const void *x, const void *weight, const void *bias, co
   p.rows = (int)rows;
   p.K = K;
   p.N = N;
-  const size_t smem = proj_smem_bytes(K, N) + 1024;  // + slack for the 1024-byte round-up in the kernel
-  auto kernel = bf16 ? value_proj_kernel<true> : value_proj_kernel<false>;
-  // opt in to > 48 KB of dynamic shared memory once per (device, instantiation)
-  static std::atomic<int> attr_set[64][2];
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return MSDA_ERR_UNSUPPORTED;
-  if (!attr_set[dev][bf16].load(std::memory_order_acquire)) {
-    const cudaError_t ae = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                (int)(proj_smem_bytes(kMaxChunks * kChunkK, kMaxN) + 1024));
-    if (ae != cudaSuccess) return (int)ae;
-    attr_set[dev][bf16].store(1, std::memory_order_release);
+  static std::atomic<int> sm_count[64];
+  int sms = sm_count[dev].load(std::memory_order_acquire);
+  if (sms == 0) {
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    sm_count[dev].store(sms, std::memory_order_release);
   }
-  const unsigned grid = (unsigned)((rows + kTileRows - 1) / kTileRows);
-  kernel<<<grid, kThreads, smem, stream>>>(map_x, map_w, map_out, p);
+  const unsigned tiles = (unsigned)((rows + kTileRows - 1) / kTileRows);
+  // opt in to > 48 KB of dynamic shared memory once per (device, kernel)
+  static std::atomic<int> attr_set[64][4];
+  auto opt_in = [&](const void *fn, int slot, size_t bytes) -> cudaError_t {
+    if (attr_set[dev][slot].load(std::memory_order_acquire)) return cudaSuccess;
+    const cudaError_t ae = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (ae == cudaSuccess) attr_set[dev][slot].store(1, std::memory_order_release);
+    return ae;
+  };
+  if (single_tile) {
+    // one tile per CTA, output staged in shared memory and written by TMA (the first version; kept for A/B runs)
+    const size_t smem = proj_smem_bytes(K, N) + 1024;  // + slack for the 1024-byte round-up in the kernel
+    auto kernel = bf16 ? value_proj_kernel<true> : value_proj_kernel<false>;
+    const cudaError_t ae = opt_in(reinterpret_cast<const void *>(kernel), bf16 ? 1 : 0, proj_smem_bytes(kMaxChunks * kChunkK, kMaxN) + 1024);
+    if (ae != cudaSuccess) return (int)ae;
+    kernel<<<tiles, kThreads, smem, stream>>>(map_x, map_w, map_out, p);
+    msda_detail::set_last_variant(bf16 ? "value_proj<bf16>/tcgen05/single-tile" : "value_proj<f16>/tcgen05/single-tile");
+  } else {
+    const size_t smem = persistent_smem_bytes(K, N) + 1024;
+    auto kernel = bf16 ? value_proj_persistent_kernel<true> : value_proj_persistent_kernel<false>;
+    const cudaError_t ae = opt_in(reinterpret_cast<const void *>(kernel), bf16 ? 3 : 2, persistent_smem_bytes(kMaxChunks * kChunkK, kMaxN) + 1024);
+    if (ae != cudaSuccess) return (int)ae;
+    const unsigned grid = tiles < (unsigned)sms ? tiles : (unsigned)sms;
+    const int wide = (((uintptr_t)value & 31u) == 0 && (N * 2) % 32 == 0) ? 1 : 0;
+    kernel<<<grid, kPersistentThreads, smem, stream>>>(map_x, map_w, p, static_cast<unsigned char *>(value), wide);
+    msda_detail::set_last_variant(bf16 ? "value_proj<bf16>/tcgen05/persistent" : "value_proj<f16>/tcgen05/persistent");
+  }
   msda_detail::launch_count.fetch_add(1, std::memory_order_relaxed);
-  msda_detail::set_last_variant(bf16 ? "value_proj<bf16>/tcgen05" : "value_proj<f16>/tcgen05");
   return (int)cudaGetLastError();
 }
 

@@ -63,6 +63,24 @@ def test_value_proj_shapes_and_optional_inputs(fin, fout, bias, mask, cuda_devic
         _check(out, _reference(x, w, b, m), dtype, m)
 
 
+@pytest.mark.parametrize("bs,keys", [(1, 100), (2, 129), (1, 40000)])
+def test_value_proj_single_tile_variant_is_bit_identical(bs, keys, cuda_device, monkeypatch):
+    """The default is the persistent, warp-specialised kernel; the one-tile-per-CTA kernel (TMA-stored output) stays
+    selectable for A/B runs.  Same MMAs in the same order: bit-identical.  40,000 rows = 313 tiles: every persistent
+    CTA walks both accumulator buffers and wraps the 5-slot ring several times."""
+    for dtype in (torch.float16, torch.bfloat16):
+        x, w, b, m = _case(cuda_device, dtype, bs, keys, 256, 256, seed=keys)
+        monkeypatch.delenv("MSDA_B200_VPROJ_SINGLE_TILE", raising=False)
+        a = cb.value_proj(x, w, b, m)
+        assert cb.last_variant().endswith("/persistent")
+        monkeypatch.setenv("MSDA_B200_VPROJ_SINGLE_TILE", "1")
+        c = cb.value_proj(x, w, b, m)
+        assert cb.last_variant().endswith("/single-tile")
+        torch.cuda.synchronize()
+        assert torch.equal(a, c)
+        _check(a, _reference(x, w, b, m), dtype, m)
+
+
 def test_value_proj_output_is_the_ops_value_layout(cuda_device):
     x, w, b, m = _case(cuda_device, torch.float16, 2, 200, 256, 256)
     v = cb.value_proj(x, w, b, m, num_heads=8)
