@@ -126,6 +126,20 @@ __device__ __forceinline__ void tmem_load_32(uint32_t taddr, uint32_t (&v)[32]) 
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// same without the wait: the caller overlaps it with work on registers it already holds, then waits
+__device__ __forceinline__ void tmem_load_32_async(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+
 template <bool BF16>
 __device__ __forceinline__ float elem_to_float(unsigned short bits) {
   if constexpr (BF16) return __uint_as_float((unsigned)bits << 16);
@@ -267,77 +281,126 @@ value_proj_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
 
 // ---------------------------------------------------------------------------
 // Persistent, warp-specialised variant (the default).  One CTA per SM loops over row tiles:
-//   warp 4  TMA producer: the weight matrix once (resident for the CTA's lifetime), then the x tiles as a ring
-//           of 64-wide K chunks (kStages x 16 KB), running ahead of the MMAs by up to kStages chunks;
-//   warp 5  MMA issuer: tcgen05.mma into one of TWO accumulator buffers in tensor memory, tcgen05.commit frees
+//   warp 8  TMA producer: the x tiles as a ring of 64-wide K chunks (kStages x 16 KB) running ahead of the
+//           MMAs, and the weight matrix once (resident for the CTA's lifetime), interleaved chunk by chunk with
+//           the first tile so the first MMAs start after 48 KB instead of 192 KB; the first loads are issued
+//           before the CTA-wide set-up barrier (they only need the mbarriers this warp initialised itself);
+//   warp 9  MMA issuer: tcgen05.mma into one of TWO accumulator buffers in tensor memory; tcgen05.commit frees
 //           each ring slot and publishes each finished accumulator;
-//   warps 0-3  epilogue: tcgen05.ld of their lane quarter, bias / mask / rounding, 32-byte stores straight to
-//           global memory (each thread owns one output row) -- so the epilogue of tile i overlaps the loads and
-//           MMAs of tile i+1, and no shared memory is spent on an output staging tile.
+//   warps 0-7  epilogue: tcgen05.ld of their lane quarter (warps w and w+4 share a quarter and split the
+//           columns), bias / mask / rounding, 16-byte conflict-free stores into a swizzled staging buffer
+//           (2 x 16 KB = 128 output columns per pass), one thread writes it back with TMA stores.  The
+//           accumulator is released as soon as its last columns are in registers, so the epilogue of tile i
+//           overlaps the loads and MMAs of tile i+1.
+// Measured phase timeline (tools/vproj_trace.py, -DMSDA_VPROJ_TRACE) is in DESIGN.md section 4.
 // ---------------------------------------------------------------------------
-constexpr int kStages = 5;
-constexpr int kPersistentThreads = (kEpilogueWarps + 2) * 32;
+#ifdef MSDA_VPROJ_TRACE
+// Debug build only: %globaltimer stamps of the phases of every CTA, read back by msda_b200_debug_vproj_trace.
+constexpr int kTraceSlots = 8;
+__device__ unsigned long long g_vproj_trace[1024][kTraceSlots];
+__device__ __forceinline__ void trace_stamp(int slot) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  if (blockIdx.x < 1024) g_vproj_trace[blockIdx.x][slot] = t;
+}
+#if MSDA_VPROJ_TRACE == 2  // epilogue detail of the first tile instead of the kernel phases
+#define VPROJ_TRACE(slot)
+#define VPROJ_TRACE_EPI(slot) trace_stamp(slot)
+#else
+#define VPROJ_TRACE(slot) trace_stamp(slot)
+#define VPROJ_TRACE_EPI(slot)
+#endif
+#else
+#define VPROJ_TRACE(slot)
+#define VPROJ_TRACE_EPI(slot)
+#endif
+
+constexpr int kStages = 4;          // x ring slots (one K chunk of one tile each)
+constexpr int kStageChunks = 2;     // output staging: two 64-column chunks per pass
+constexpr int kPEpilogueWarps = 8;
+constexpr int kProducerWarp = kPEpilogueWarps, kMmaWarp = kPEpilogueWarps + 1;
+constexpr int kPersistentThreads = (kPEpilogueWarps + 2) * 32;
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-
-__device__ __forceinline__ void store_32B(void *dst, const unsigned (&w)[8], bool wide) {
-  if (wide) {
-    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
-                 "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
-                 : "memory");
-  } else {
-    reinterpret_cast<uint4 *>(dst)[0] = make_uint4(w[0], w[1], w[2], w[3]);
-    reinterpret_cast<uint4 *>(dst)[1] = make_uint4(w[4], w[5], w[6], w[7]);
-  }
+__device__ __forceinline__ void epilogue_barrier() {  // the 8 epilogue warps only (named barrier 1)
+  asm volatile("bar.sync 1, %0;" ::"n"(kPEpilogueWarps * 32) : "memory");
 }
 
-// Dynamic shared memory (1024-byte aligned): weight chunks (K/64 x N x 128 B), x ring (kStages x 16 KB),
-// bias as fp32 [N], barriers, TMEM base address.
+// Dynamic shared memory (1024-byte aligned): weight chunks (K/64 x N x 128 B), x ring (kStages x 16 KB), output
+// staging (kStageChunks x 16 KB), bias as fp32 [N], barriers, TMEM base address.
 template <bool BF16>
 __global__ void __launch_bounds__(kPersistentThreads, 1)
-value_proj_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const ProjParams p,
-                             unsigned char *__restrict__ out, int wide_stores) {
+value_proj_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                             const __grid_constant__ CUtensorMap map_out, const ProjParams p, int pdl) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int chunks = p.K / kChunkK;
+  const int out_chunks = p.N / kChunkK;
   unsigned char *w_tile = smem;
   unsigned char *ring = smem + (size_t)chunks * p.N * 128;
-  float *bias_f = reinterpret_cast<float *>(ring + (size_t)kStages * kTileRows * 128);
-  uint64_t *w_full = reinterpret_cast<uint64_t *>(bias_f + kMaxN);
-  uint64_t *a_full = w_full + 1;            // [kStages]
+  unsigned char *staging = ring + (size_t)kStages * kTileRows * 128;
+  float *bias_f = reinterpret_cast<float *>(staging + (size_t)kStageChunks * kTileRows * 128);
+  uint64_t *w_full = reinterpret_cast<uint64_t *>(bias_f + kMaxN);  // [kMaxChunks]
+  uint64_t *a_full = w_full + kMaxChunks;   // [kStages]
   uint64_t *a_empty = a_full + kStages;     // [kStages]
   uint64_t *acc_full = a_empty + kStages;   // [2]
   uint64_t *acc_empty = acc_full + 2;       // [2]
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
 
   const int warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31);
+  if (threadIdx.x == 0) VPROJ_TRACE(0);  // kernel entry
   const int tiles = (p.rows + kTileRows - 1) / kTileRows;
   const uint32_t acc_cols = p.N <= 32 ? 32u : p.N <= 64 ? 64u : p.N <= 128 ? 128u : 256u;  // per accumulator buffer
   const uint32_t tmem_cols = 2 * acc_cols;
 
-  if (warp == kEpilogueWarps) {
+  // producer state (lives across the set-up barrier)
+  int p_stage = 0;
+  unsigned p_phase = 0;
+  auto load_x_chunk = [&](int tile, int c) {
+    mbar_wait(&a_empty[p_stage], p_phase ^ 1u);  // a fresh barrier passes the wait on the opposite parity
+    mbar_expect_tx(&a_full[p_stage], (unsigned)(kTileRows * 128));
+    tma_load_2d(ring + (size_t)p_stage * kTileRows * 128, &map_x, c * kChunkK, tile * kTileRows, &a_full[p_stage]);
+    if (++p_stage == kStages) {
+      p_stage = 0;
+      p_phase ^= 1u;
+    }
+  };
+
+  if (warp == kProducerWarp) {
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
-      mbar_init(w_full, 1);
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_out) : "memory");
+      for (int c = 0; c < kMaxChunks; ++c) mbar_init(&w_full[c], 1);
       for (int s = 0; s < kStages; ++s) {
         mbar_init(&a_full[s], 1);
         mbar_init(&a_empty[s], 1);
       }
       for (int b = 0; b < 2; ++b) {
         mbar_init(&acc_full[b], 1);
-        mbar_init(&acc_empty[b], kEpilogueWarps);
+        mbar_init(&acc_empty[b], kPEpilogueWarps);
       }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      // first tile + weights, chunk by chunk, before the rest of the CTA has finished its set-up
+      if (pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
+      if ((int)blockIdx.x < tiles) {
+        for (int c = 0; c < chunks; ++c) {
+          load_x_chunk((int)blockIdx.x, c);
+          mbar_expect_tx(&w_full[c], (unsigned)(p.N * 128));
+          tma_load_2d(w_tile + (size_t)c * p.N * 128, &map_w, c * kChunkK, 0, &w_full[c]);
+        }
+      }
     }
-  } else if (warp == kEpilogueWarps + 1) {
+    __syncwarp();
+  } else if (warp == kMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   } else {
-    for (int n = (int)threadIdx.x; n < p.N; n += kEpilogueWarps * 32) {
+    if (pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
+    for (int n = (int)threadIdx.x; n < p.N; n += kPEpilogueWarps * 32) {
       bias_f[n] = p.bias ? elem_to_float<BF16>(static_cast<const unsigned short *>(p.bias)[n]) : 0.f;
     }
   }
@@ -345,33 +408,24 @@ value_proj_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) VPROJ_TRACE(1);  // set-up done (barriers, TMEM, bias)
+  // let the next kernel of the stream start its own launch / set-up (it waits for our memory in its own
+  // griddepcontrol.wait; kernels launched without the attribute are unaffected)
+  if (pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
-  if (warp == kEpilogueWarps) {
-    // ===== TMA producer =====
+  if (warp == kProducerWarp) {
+    // ===== TMA producer: the remaining tiles =====
     if (lane == 0) {
-      mbar_expect_tx(w_full, (unsigned)(chunks * p.N * 128));
-      for (int c = 0; c < chunks; ++c) tma_load_2d(w_tile + (size_t)c * p.N * 128, &map_w, c * kChunkK, 0, w_full);
-      int stage = 0;
-      unsigned phase = 0;
-      for (int tile = (int)blockIdx.x; tile < tiles; tile += (int)gridDim.x) {
-        for (int c = 0; c < chunks; ++c) {
-          mbar_wait(&a_empty[stage], phase ^ 1u);  // a fresh barrier passes the wait on the opposite parity
-          mbar_expect_tx(&a_full[stage], (unsigned)(kTileRows * 128));
-          tma_load_2d(ring + (size_t)stage * kTileRows * 128, &map_x, c * kChunkK, tile * kTileRows, &a_full[stage]);
-          if (++stage == kStages) {
-            stage = 0;
-            phase ^= 1u;
-          }
-        }
+      for (int tile = (int)blockIdx.x + (int)gridDim.x; tile < tiles; tile += (int)gridDim.x) {
+        for (int c = 0; c < chunks; ++c) load_x_chunk(tile, c);
       }
     }
     __syncwarp();
-  } else if (warp == kEpilogueWarps + 1) {
+  } else if (warp == kMmaWarp) {
     // ===== MMA issuer =====
     if (lane == 0) {
       const uint32_t fmt = BF16 ? 1u : 0u;
       const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.N >> 3) << 17) | ((uint32_t)(kTileRows >> 4) << 24);
-      mbar_wait(w_full, 0);
       int stage = 0;
       unsigned phase = 0;
       int t = 0;
@@ -381,7 +435,12 @@ value_proj_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t acc = tmem_base + (uint32_t)buf * acc_cols;
         for (int c = 0; c < chunks; ++c) {
+          if (t == 0) {
+            mbar_wait(&w_full[c], 0);
+            if (c == 0) VPROJ_TRACE(2);  // first weight chunk landed
+          }
           mbar_wait(&a_full[stage], phase);
+          if (t == 0 && c == 0) VPROJ_TRACE(3);  // first x chunk landed
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t a_addr = smem_u32(ring + (size_t)stage * kTileRows * 128);
           const uint32_t b_addr = smem_u32(w_tile + (size_t)c * p.N * 128);
@@ -397,56 +456,100 @@ value_proj_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __
           }
         }
         umma_commit(&acc_full[buf]);
+        if (t == 0) VPROJ_TRACE(4);  // first tile's MMAs issued
       }
     }
     __syncwarp();
   } else {
     // ===== epilogue =====
-    const int rl = warp * 32 + lane;
-    const size_t row_bytes = (size_t)p.N * 2;
+    // warp w reads TMEM lanes [32*(w%4), +32) (the hardware ties a warp to that lane quarter); warps w and w+4
+    // share a quarter: in every pass warp-half h converts output chunk 2*pass + h (64 columns) into staging
+    // chunk h.  The TMEM load of the second 32 columns is in flight while the first 32 are converted.
+    const int quarter = warp & 3, half = warp >> 2;
+    const int rl = quarter * 32 + lane;
+    const int passes = (out_chunks + kStageChunks - 1) / kStageChunks;
+    unsigned char *my_stage_row = staging + (size_t)half * kTileRows * 128 + (size_t)rl * 128;
     int t = 0;
     for (int tile = (int)blockIdx.x; tile < tiles; tile += (int)gridDim.x, ++t) {
       const int buf = t & 1;
       const int r = tile * kTileRows + rl;
-      const bool in_range = r < p.rows;
-      const bool padded = p.mask != nullptr && in_range && p.mask[r] != 0;
+      const bool padded = p.mask != nullptr && r < p.rows && p.mask[r] != 0;
       mbar_wait(&acc_full[buf], ((unsigned)t >> 1) & 1u);
+      if (t == 0 && threadIdx.x == 0) VPROJ_TRACE(5);  // first accumulator complete
+      if (t == 0 && threadIdx.x == 0) VPROJ_TRACE_EPI(0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t acc = tmem_base + (uint32_t)buf * acc_cols + ((uint32_t)(warp * 32) << 16);
-      unsigned char *orow = out + (size_t)r * row_bytes;
-      for (int c32 = 0; c32 < p.N / 32; ++c32) {
-        uint32_t v[32];
-        tmem_load_32(acc + (uint32_t)(c32 * 32), v);
+      const uint32_t acc = tmem_base + (uint32_t)buf * acc_cols + ((uint32_t)(quarter * 32) << 16);
+      for (int pass = 0; pass < passes; ++pass) {
+        const bool tr = t == 0 && threadIdx.x == 0 && pass == 0;
+        const int oc = pass * kStageChunks + half;  // this warp's output chunk (64 columns)
+        const bool active = oc < out_chunks;
+        uint32_t v0[32], v1[32];  // named (not indexed) so they stay in registers
+        if (active) {
+          tmem_load_32_async(acc + (uint32_t)(oc * 64), v0);
+          tmem_load_32_async(acc + (uint32_t)(oc * 64 + 32), v1);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        }
+        if (tr) VPROJ_TRACE_EPI(1);
+        if (pass == passes - 1) {
+          // the accumulator is in registers: hand the buffer back to the MMA issuer
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        }
+        epilogue_barrier();  // the previous pass's TMA stores have finished reading the staging buffer
+        if (tr) VPROJ_TRACE_EPI(2);
+        if (active) {
+          auto emit = [&](const uint32_t(&cur)[32], int g) {  // g: which 32-column half of the chunk
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {  // two 32-byte pieces = 16 elements each
-          unsigned ow[8];
+            for (int i = 0; i < 4; ++i) {  // four 16-byte pieces = 8 elements each
+              uint4 o;
+              unsigned *ow = reinterpret_cast<unsigned *>(&o);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int col = c32 * 32 + i * 16 + j * 2;
-            const float a = padded ? 0.f : __uint_as_float(v[i * 16 + j * 2]) + bias_f[col];
-            const float b = padded ? 0.f : __uint_as_float(v[i * 16 + j * 2 + 1]) + bias_f[col + 1];
-            ow[j] = pack_pair<BF16>(a, b);
+              for (int j = 0; j < 4; ++j) {
+                const int col = oc * 64 + g * 32 + i * 8 + j * 2;
+                const float a = padded ? 0.f : __uint_as_float(cur[i * 8 + j * 2]) + bias_f[col];
+                const float b = padded ? 0.f : __uint_as_float(cur[i * 8 + j * 2 + 1]) + bias_f[col + 1];
+                ow[j] = pack_pair<BF16>(a, b);
+              }
+              const int piece = g * 4 + i;
+              *reinterpret_cast<uint4 *>(my_stage_row + ((piece ^ (rl & 7)) << 4)) = o;
+            }
+          };
+          emit(v0, 0);
+          emit(v1, 1);
+        }
+        // generic-proxy writes -> visible to the TMA (async proxy), then one thread stores the chunks
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (tr) VPROJ_TRACE_EPI(3);
+        epilogue_barrier();
+        if (tr) VPROJ_TRACE_EPI(4);
+        if (threadIdx.x == 0) {
+          for (int h = 0; h < kStageChunks; ++h) {
+            const int c = pass * kStageChunks + h;
+            if (c < out_chunks) tma_store_2d(&map_out, staging + (size_t)h * kTileRows * 128, c * kChunkK, tile * kTileRows);
           }
-          if (in_range) store_32B(orow + (size_t)c32 * 64 + i * 32, ow, wide_stores != 0);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          if (tr) VPROJ_TRACE_EPI(5);
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // staging may be overwritten after this
+          if (tr) VPROJ_TRACE_EPI(6);
         }
       }
-      // this warp has read its quarter of the accumulator: hand the buffer back to the MMA issuer
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      if (t == 0 && threadIdx.x == 0) VPROJ_TRACE_EPI(7);
+      if (t == 0 && threadIdx.x == 0) VPROJ_TRACE(6);  // first tile handed to the TMA
     }
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == kEpilogueWarps + 1) {
+  if (warp == kMmaWarp) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }
+  if (threadIdx.x == 0) VPROJ_TRACE(7);  // exit
 }
 
 size_t persistent_smem_bytes(int K, int N) {
-  return (size_t)(K / kChunkK) * N * 128 + (size_t)kStages * kTileRows * 128 + kMaxN * sizeof(float) +
-         (1 + 2 * kStages + 4) * sizeof(uint64_t) + 16;
+  return (size_t)(K / kChunkK) * N * 128 + (size_t)(kStages + kStageChunks) * kTileRows * 128 + kMaxN * sizeof(float) +
+         (kMaxChunks + 2 * kStages + 4) * sizeof(uint64_t) + 16;
 }
 
 // ---------------------------------------------------------------------------
@@ -519,7 +622,7 @@ int msda_b200_value_proj(const void *x, const void *weight, const void *bias, co
   const bool single_tile = single && *single == '1';
   CUtensorMap map_x, map_w, map_out;
   if (!make_map(&map_x, x, bf16, (uint64_t)K, (uint64_t)rows, kTileRows) || !make_map(&map_w, weight, bf16, (uint64_t)K, (uint64_t)N, (uint32_t)N) ||
-      (single_tile && !make_map(&map_out, value, bf16, (uint64_t)N, (uint64_t)rows, kTileRows))) {
+      !make_map(&map_out, value, bf16, (uint64_t)N, (uint64_t)rows, kTileRows)) {
     return MSDA_ERR_UNSUPPORTED;
   }
   ProjParams p;
@@ -559,12 +662,34 @@ int msda_b200_value_proj(const void *x, const void *weight, const void *bias, co
     const cudaError_t ae = opt_in(reinterpret_cast<const void *>(kernel), bf16 ? 3 : 2, persistent_smem_bytes(kMaxChunks * kChunkK, kMaxN) + 1024);
     if (ae != cudaSuccess) return (int)ae;
     const unsigned grid = tiles < (unsigned)sms ? tiles : (unsigned)sms;
-    const int wide = (((uintptr_t)value & 31u) == 0 && (N * 2) % 32 == 0) ? 1 : 0;
-    kernel<<<grid, kPersistentThreads, smem, stream>>>(map_x, map_w, p, static_cast<unsigned char *>(value), wide);
+    // programmatic dependent launch: this kernel's set-up overlaps the tail of the previous kernel of the
+    // stream, and it releases its own dependents right after set-up (MSDA_B200_PDL=0 launches the plain way)
+    const char *pdl_env = getenv("MSDA_B200_PDL");
+    const int pdl = (pdl_env && *pdl_env == '0') ? 0 : 1;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kPersistentThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    const cudaError_t le = cudaLaunchKernelEx(&cfg, kernel, map_x, map_w, map_out, p, pdl);
+    if (le != cudaSuccess) return (int)le;
     msda_detail::set_last_variant(bf16 ? "value_proj<bf16>/tcgen05/persistent" : "value_proj<f16>/tcgen05/persistent");
   }
   msda_detail::launch_count.fetch_add(1, std::memory_order_relaxed);
   return (int)cudaGetLastError();
 }
+
+#ifdef MSDA_VPROJ_TRACE
+int msda_b200_debug_vproj_trace(unsigned long long *host_out, int ctas) {
+  if (ctas > 1024) ctas = 1024;
+  return (int)cudaMemcpyFromSymbol(host_out, g_vproj_trace, sizeof(unsigned long long) * kTraceSlots * (size_t)ctas);
+}
+#endif
 
 }  // extern "C"
