@@ -288,10 +288,10 @@ value_proj_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
 //   warp 9  MMA issuer: tcgen05.mma into one of TWO accumulator buffers in tensor memory; tcgen05.commit frees
 //           each ring slot and publishes each finished accumulator;
 //   warps 0-7  epilogue: tcgen05.ld of their lane quarter (warps w and w+4 share a quarter and split the
-//           columns), bias / mask / rounding, 16-byte conflict-free stores into a swizzled staging buffer
-//           (2 x 16 KB = 128 output columns per pass), one thread writes it back with TMA stores.  The
-//           accumulator is released as soon as its last columns are in registers, so the epilogue of tile i
-//           overlaps the loads and MMAs of tile i+1.
+//           columns), bias / mask / rounding, 16-byte conflict-free stores into the warp's own 4 KB swizzled
+//           staging slab, written back by the warp's own TMA store (no CTA-wide barrier).  The accumulator is
+//           released as soon as its last columns are in registers, so the epilogue of tile i overlaps the
+//           loads and MMAs of tile i+1.
 // Measured phase timeline (tools/vproj_trace.py, -DMSDA_VPROJ_TRACE) is in DESIGN.md section 4.
 // ---------------------------------------------------------------------------
 #ifdef MSDA_VPROJ_TRACE
@@ -316,16 +316,13 @@ __device__ __forceinline__ void trace_stamp(int slot) {
 #endif
 
 constexpr int kStages = 4;          // x ring slots (one K chunk of one tile each)
-constexpr int kStageChunks = 2;     // output staging: two 64-column chunks per pass
+constexpr int kStageChunks = 2;     // output staging: 2 x 16 KB = one 4 KB slab (32 rows x 64 columns) per epilogue warp
 constexpr int kPEpilogueWarps = 8;
 constexpr int kProducerWarp = kPEpilogueWarps, kMmaWarp = kPEpilogueWarps + 1;
 constexpr int kPersistentThreads = (kPEpilogueWarps + 2) * 32;
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void epilogue_barrier() {  // the 8 epilogue warps only (named barrier 1)
-  asm volatile("bar.sync 1, %0;" ::"n"(kPEpilogueWarps * 32) : "memory");
 }
 
 // Dynamic shared memory (1024-byte aligned): weight chunks (K/64 x N x 128 B), x ring (kStages x 16 KB), output
@@ -463,12 +460,14 @@ value_proj_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __
   } else {
     // ===== epilogue =====
     // warp w reads TMEM lanes [32*(w%4), +32) (the hardware ties a warp to that lane quarter); warps w and w+4
-    // share a quarter: in every pass warp-half h converts output chunk 2*pass + h (64 columns) into staging
-    // chunk h.  The TMEM load of the second 32 columns is in flight while the first 32 are converted.
+    // share a quarter and split the 64-column output chunks between them (even / odd).  Every warp owns a 4 KB
+    // slab of the staging buffer (its 32 rows x 64 columns, 128-byte swizzled) and writes it back with its own
+    // TMA store, so the eight warps never wait for each other: no CTA-wide barrier in the epilogue, and a slab's
+    // TMA read overlaps the TMEM load and the conversion of the warp's next chunk.
     const int quarter = warp & 3, half = warp >> 2;
     const int rl = quarter * 32 + lane;
-    const int passes = (out_chunks + kStageChunks - 1) / kStageChunks;
-    unsigned char *my_stage_row = staging + (size_t)half * kTileRows * 128 + (size_t)rl * 128;
+    unsigned char *slab = staging + (size_t)warp * (32 * 128);
+    unsigned char *slab_row = slab + (size_t)lane * 128;
     int t = 0;
     for (int tile = (int)blockIdx.x; tile < tiles; tile += (int)gridDim.x, ++t) {
       const int buf = t & 1;
@@ -479,64 +478,57 @@ value_proj_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __
       if (t == 0 && threadIdx.x == 0) VPROJ_TRACE_EPI(0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t acc = tmem_base + (uint32_t)buf * acc_cols + ((uint32_t)(quarter * 32) << 16);
-      for (int pass = 0; pass < passes; ++pass) {
-        const bool tr = t == 0 && threadIdx.x == 0 && pass == 0;
-        const int oc = pass * kStageChunks + half;  // this warp's output chunk (64 columns)
-        const bool active = oc < out_chunks;
+      for (int oc = half; oc < out_chunks; oc += 2) {  // this warp's output chunks (64 columns each)
+        const bool tr = t == 0 && threadIdx.x == 0 && oc == half;
         uint32_t v0[32], v1[32];  // named (not indexed) so they stay in registers
-        if (active) {
-          tmem_load_32_async(acc + (uint32_t)(oc * 64), v0);
-          tmem_load_32_async(acc + (uint32_t)(oc * 64 + 32), v1);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        }
+        tmem_load_32_async(acc + (uint32_t)(oc * 64), v0);
+        tmem_load_32_async(acc + (uint32_t)(oc * 64 + 32), v1);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (tr) VPROJ_TRACE_EPI(1);
-        if (pass == passes - 1) {
-          // the accumulator is in registers: hand the buffer back to the MMA issuer
+        if (oc + 2 >= out_chunks) {
+          // the warp's share of the accumulator is in registers: hand the buffer back to the MMA issuer
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[buf]);
         }
-        epilogue_barrier();  // the previous pass's TMA stores have finished reading the staging buffer
+        // the slab's previous TMA store (issued by lane 0) must have finished reading it
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
         if (tr) VPROJ_TRACE_EPI(2);
-        if (active) {
-          auto emit = [&](const uint32_t(&cur)[32], int g) {  // g: which 32-column half of the chunk
+        auto emit = [&](const uint32_t(&cur)[32], int g) {  // g: which 32-column half of the chunk
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {  // four 16-byte pieces = 8 elements each
-              uint4 o;
-              unsigned *ow = reinterpret_cast<unsigned *>(&o);
+          for (int i = 0; i < 4; ++i) {  // four 16-byte pieces = 8 elements each
+            const float4 b0 = *reinterpret_cast<const float4 *>(bias_f + oc * 64 + g * 32 + i * 8);
+            const float4 b1 = *reinterpret_cast<const float4 *>(bias_f + oc * 64 + g * 32 + i * 8 + 4);
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            uint4 o;
+            unsigned *ow = reinterpret_cast<unsigned *>(&o);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const int col = oc * 64 + g * 32 + i * 8 + j * 2;
-                const float a = padded ? 0.f : __uint_as_float(cur[i * 8 + j * 2]) + bias_f[col];
-                const float b = padded ? 0.f : __uint_as_float(cur[i * 8 + j * 2 + 1]) + bias_f[col + 1];
-                ow[j] = pack_pair<BF16>(a, b);
-              }
-              const int piece = g * 4 + i;
-              *reinterpret_cast<uint4 *>(my_stage_row + ((piece ^ (rl & 7)) << 4)) = o;
+            for (int j = 0; j < 4; ++j) {
+              const float a = padded ? 0.f : __uint_as_float(cur[i * 8 + j * 2]) + bb[j * 2];
+              const float b = padded ? 0.f : __uint_as_float(cur[i * 8 + j * 2 + 1]) + bb[j * 2 + 1];
+              ow[j] = pack_pair<BF16>(a, b);
             }
-          };
-          emit(v0, 0);
-          emit(v1, 1);
-        }
-        // generic-proxy writes -> visible to the TMA (async proxy), then one thread stores the chunks
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        if (tr) VPROJ_TRACE_EPI(3);
-        epilogue_barrier();
-        if (tr) VPROJ_TRACE_EPI(4);
-        if (threadIdx.x == 0) {
-          for (int h = 0; h < kStageChunks; ++h) {
-            const int c = pass * kStageChunks + h;
-            if (c < out_chunks) tma_store_2d(&map_out, staging + (size_t)h * kTileRows * 128, c * kChunkK, tile * kTileRows);
+            const int piece = g * 4 + i;
+            *reinterpret_cast<uint4 *>(slab_row + ((piece ^ (lane & 7)) << 4)) = o;
           }
+        };
+        emit(v0, 0);
+        emit(v1, 1);
+        // generic-proxy writes -> visible to the TMA (async proxy), then lane 0 stores the slab
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (tr) VPROJ_TRACE_EPI(3);
+        if (lane == 0) {
+          tma_store_2d(&map_out, slab, oc * kChunkK, tile * kTileRows + quarter * 32);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          if (tr) VPROJ_TRACE_EPI(5);
-          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // staging may be overwritten after this
-          if (tr) VPROJ_TRACE_EPI(6);
         }
+        if (tr) VPROJ_TRACE_EPI(4);
       }
-      if (t == 0 && threadIdx.x == 0) VPROJ_TRACE_EPI(7);
       if (t == 0 && threadIdx.x == 0) VPROJ_TRACE(6);  // first tile handed to the TMA
+      if (t == 0 && threadIdx.x == 0) VPROJ_TRACE_EPI(7);
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem must outlive the reads
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -622,7 +614,8 @@ int msda_b200_value_proj(const void *x, const void *weight, const void *bias, co
   const bool single_tile = single && *single == '1';
   CUtensorMap map_x, map_w, map_out;
   if (!make_map(&map_x, x, bf16, (uint64_t)K, (uint64_t)rows, kTileRows) || !make_map(&map_w, weight, bf16, (uint64_t)K, (uint64_t)N, (uint32_t)N) ||
-      !make_map(&map_out, value, bf16, (uint64_t)N, (uint64_t)rows, kTileRows)) {
+      // output boxes: a whole 128-row chunk for the single-tile kernel, one warp's 32 rows for the persistent one
+      !make_map(&map_out, value, bf16, (uint64_t)N, (uint64_t)rows, single_tile ? kTileRows : 32)) {
     return MSDA_ERR_UNSUPPORTED;
   }
   ProjParams p;
