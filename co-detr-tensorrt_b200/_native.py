@@ -51,6 +51,7 @@ EXPORTED_SYMBOLS = [
     "msda_b200_read_probe",
     "msda_b200_value_proj_supported",
     "msda_b200_value_proj",
+    "msda_b200_output_proj",
 ]
 
 DTYPE_F32, DTYPE_F16, DTYPE_BF16, DTYPE_F64 = 0, 1, 2, 3
@@ -190,6 +191,8 @@ def load() -> ctypes.CDLL:
     lib.msda_b200_value_proj_supported.argtypes = [i64, i64, ci]
     lib.msda_b200_value_proj.restype = ci
     lib.msda_b200_value_proj.argtypes = [vp, vp, vp, vp, vp, i64, i64, i64, ci, cu, vp]
+    lib.msda_b200_output_proj.restype = ci
+    lib.msda_b200_output_proj.argtypes = [vp, vp, vp, vp, vp, i64, i64, i64, ci, cu, vp]
     if lib.msda_b200_abi_version() != 1:
         raise NativeLibraryError("libmsda_b200.so ABI version mismatch; rebuild it")
     _lib = lib

@@ -48,6 +48,7 @@ constexpr int kThreads = (kEpilogueWarps + 1) * 32;  // + one producer / MMA war
 struct ProjParams {
   const void *bias;            // [N] in the element type, or nullptr
   const unsigned char *mask;   // [rows], non-zero = padded key (row of zeros), or nullptr
+  const void *residual;        // [rows, N] in the element type, added after the bias, or nullptr (output_proj mode)
   int rows, K, N;
 };
 
@@ -473,6 +474,8 @@ value_proj_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __
       const int buf = t & 1;
       const int r = tile * kTileRows + rl;
       const bool padded = p.mask != nullptr && r < p.rows && p.mask[r] != 0;
+      const unsigned char *res_row =
+          (p.residual != nullptr && r < p.rows) ? static_cast<const unsigned char *>(p.residual) + (size_t)r * p.N * 2 : nullptr;
       mbar_wait(&acc_full[buf], ((unsigned)t >> 1) & 1u);
       if (t == 0 && threadIdx.x == 0) VPROJ_TRACE(5);  // first accumulator complete
       if (t == 0 && threadIdx.x == 0) VPROJ_TRACE_EPI(0);
@@ -501,12 +504,22 @@ value_proj_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __
             const float4 b0 = *reinterpret_cast<const float4 *>(bias_f + oc * 64 + g * 32 + i * 8);
             const float4 b1 = *reinterpret_cast<const float4 *>(bias_f + oc * 64 + g * 32 + i * 8 + 4);
             const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            uint4 res = make_uint4(0u, 0u, 0u, 0u);
+            if (res_row != nullptr) res = __ldg(reinterpret_cast<const uint4 *>(res_row + (size_t)(oc * 64 + g * 32 + i * 8) * 2));
+            const unsigned rw[4] = {res.x, res.y, res.z, res.w};
             uint4 o;
             unsigned *ow = reinterpret_cast<unsigned *>(&o);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const float a = padded ? 0.f : __uint_as_float(cur[i * 8 + j * 2]) + bb[j * 2];
-              const float b = padded ? 0.f : __uint_as_float(cur[i * 8 + j * 2 + 1]) + bb[j * 2 + 1];
+              // Linear output rounded to the element type first, then the residual added and rounded again: the
+              // same two roundings as output_proj followed by a separate add in 16 bits
+              float a = padded ? 0.f : __uint_as_float(cur[i * 8 + j * 2]) + bb[j * 2];
+              float b = padded ? 0.f : __uint_as_float(cur[i * 8 + j * 2 + 1]) + bb[j * 2 + 1];
+              if (res_row != nullptr) {
+                const unsigned lin = pack_pair<BF16>(a, b);
+                a = elem_to_float<BF16>((unsigned short)(lin & 0xffffu)) + elem_to_float<BF16>((unsigned short)(rw[j] & 0xffffu));
+                b = elem_to_float<BF16>((unsigned short)(lin >> 16)) + elem_to_float<BF16>((unsigned short)(rw[j] >> 16));
+              }
               ow[j] = pack_pair<BF16>(a, b);
             }
             const int piece = g * 4 + i;
@@ -595,9 +608,9 @@ int msda_b200_value_proj_supported(int64_t in_features, int64_t out_features, in
              : 0;
 }
 
-int msda_b200_value_proj(const void *x, const void *weight, const void *bias, const unsigned char *key_padding_mask, void *value,
-                         int64_t rows, int64_t in_features, int64_t out_features, int dtype, unsigned flags, void *stream_) {
-  (void)flags;
+static int launch_projection(const void *x, const void *weight, const void *bias, const unsigned char *key_padding_mask,
+                             const void *residual, void *value, int64_t rows, int64_t in_features, int64_t out_features, int dtype,
+                             void *stream_) {
   if (rows < 0 || in_features <= 0 || out_features <= 0) return MSDA_ERR_BAD_SHAPE;
   if (dtype != MSDA_F16 && dtype != MSDA_BF16 && dtype != MSDA_F32 && dtype != MSDA_F64) return MSDA_ERR_BAD_DTYPE;
   if (!msda_b200_value_proj_supported(in_features, out_features, dtype)) return MSDA_ERR_UNSUPPORTED;
@@ -606,12 +619,13 @@ int msda_b200_value_proj(const void *x, const void *weight, const void *bias, co
   if (!x || !weight || !value) return MSDA_ERR_NULL_POINTER;
   if (((uintptr_t)x | (uintptr_t)weight | (uintptr_t)value) & 15u) return MSDA_ERR_UNSUPPORTED;  // TMA base alignment
   if (bias && ((uintptr_t)bias & 1u)) return MSDA_ERR_UNSUPPORTED;
+  if (residual && ((uintptr_t)residual & 15u)) return MSDA_ERR_UNSUPPORTED;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const bool bf16 = dtype == MSDA_BF16;
   const int K = (int)in_features, N = (int)out_features;
 
   const char *single = getenv("MSDA_B200_VPROJ_SINGLE_TILE");
-  const bool single_tile = single && *single == '1';
+  const bool single_tile = single && *single == '1' && residual == nullptr;
   CUtensorMap map_x, map_w, map_out;
   if (!make_map(&map_x, x, bf16, (uint64_t)K, (uint64_t)rows, kTileRows) || !make_map(&map_w, weight, bf16, (uint64_t)K, (uint64_t)N, (uint32_t)N) ||
       // output boxes: a whole 128-row chunk for the single-tile kernel, one warp's 32 rows for the persistent one
@@ -621,6 +635,7 @@ int msda_b200_value_proj(const void *x, const void *weight, const void *bias, co
   ProjParams p;
   p.bias = bias;
   p.mask = key_padding_mask;
+  p.residual = residual;
   p.rows = (int)rows;
   p.K = K;
   p.N = N;
@@ -672,10 +687,24 @@ int msda_b200_value_proj(const void *x, const void *weight, const void *bias, co
     cfg.numAttrs = pdl ? 1 : 0;
     const cudaError_t le = cudaLaunchKernelEx(&cfg, kernel, map_x, map_w, map_out, p, pdl);
     if (le != cudaSuccess) return (int)le;
-    msda_detail::set_last_variant(bf16 ? "value_proj<bf16>/tcgen05/persistent" : "value_proj<f16>/tcgen05/persistent");
+    if (residual) msda_detail::set_last_variant(bf16 ? "output_proj<bf16>/tcgen05/persistent" : "output_proj<f16>/tcgen05/persistent");
+    else msda_detail::set_last_variant(bf16 ? "value_proj<bf16>/tcgen05/persistent" : "value_proj<f16>/tcgen05/persistent");
   }
   msda_detail::launch_count.fetch_add(1, std::memory_order_relaxed);
   return (int)cudaGetLastError();
+}
+
+int msda_b200_value_proj(const void *x, const void *weight, const void *bias, const unsigned char *key_padding_mask, void *value,
+                         int64_t rows, int64_t in_features, int64_t out_features, int dtype, unsigned flags, void *stream) {
+  (void)flags;
+  return launch_projection(x, weight, bias, key_padding_mask, nullptr, value, rows, in_features, out_features, dtype, stream);
+}
+
+int msda_b200_output_proj(const void *attended, const void *weight, const void *bias, const void *residual, void *out, int64_t rows,
+                          int64_t in_features, int64_t out_features, int dtype, unsigned flags, void *stream) {
+  (void)flags;
+  if (rows > 0 && !residual) return MSDA_ERR_NULL_POINTER;
+  return launch_projection(attended, weight, bias, nullptr, residual, out, rows, in_features, out_features, dtype, stream);
 }
 
 #ifdef MSDA_VPROJ_TRACE

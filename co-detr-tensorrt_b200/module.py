@@ -8,7 +8,8 @@ the op can be exercised in its calling context here (same constructor arguments,
 loads, same forward signature and shape conventions); (2) ``fused_producers=True`` routes the softmax and the
 sampling-location arithmetic (:180-200) into the kernel through ``msda_b200_forward_fused`` instead of running
 them as separate PyTorch ops, and ``fused_value_proj=True`` replaces ``value_proj`` +
-``masked_fill`` (:173-176) by the tensor-core kernel ``msda_b200_value_proj`` (section 8(f).4).
+``masked_fill`` (:173-176) by the tensor-core kernel ``msda_b200_value_proj`` (section 8(f).4); ``fused_output_proj=True``
+does the same for ``output_proj`` + residual (:212-218, inference mode) with ``msda_b200_output_proj``.
 
 Differences, both deliberate: CPU tensors raise (the reference falls back to
 ``multi_scale_deformable_attention_pytorch`` at :207-210; this package has no CPU path), and ``norm_cfg`` /
@@ -28,12 +29,12 @@ from . import ops
 
 class MultiScaleDeformableAttention(nn.Module):
     """Constructor arguments, parameter names and the forward contract are the reference's (see the module
-    docstring); ``fused_producers`` and ``fused_value_proj`` are the only additions."""
+    docstring); ``fused_producers``, ``fused_value_proj`` and ``fused_output_proj`` are the only additions."""
 
     def __init__(self, embed_dims: int = 256, num_heads: int = 8, num_levels: int = 4, num_points: int = 4,
                  im2col_step: int = 64, dropout: float = 0.1, batch_first: bool = False, norm_cfg: Optional[dict] = None,
                  init_cfg: Optional[dict] = None, value_proj_ratio: float = 1.0, fused_producers: bool = False,
-                 fused_value_proj: bool = False):
+                 fused_value_proj: bool = False, fused_output_proj: bool = False):
         super().__init__()
         per_head, rem = divmod(embed_dims, num_heads)
         if rem:  # reference :56-57
@@ -42,7 +43,8 @@ class MultiScaleDeformableAttention(nn.Module):
             warnings.warn(f"{per_head} channels per head is not a power of two: the op falls back to its generic kernel")
         for name, val in dict(embed_dims=embed_dims, num_heads=num_heads, num_levels=num_levels, num_points=num_points,
                               im2col_step=im2col_step, batch_first=batch_first, norm_cfg=norm_cfg,
-                              fused_producers=fused_producers, fused_value_proj=fused_value_proj).items():
+                              fused_producers=fused_producers, fused_value_proj=fused_value_proj,
+                              fused_output_proj=fused_output_proj).items():
             setattr(self, name, val)
         samples = num_heads * num_levels * num_points
         inner = int(embed_dims * value_proj_ratio)
@@ -130,7 +132,15 @@ class MultiScaleDeformableAttention(nn.Module):
             attended = torch.ops.codetr.multi_scale_deformable_attention(
                 keys.contiguous(), spatial_shapes, level_start_index, locations, weights, self.im2col_step)
 
-        out = self.output_proj(attended)
+        lin = self.output_proj
+        if (self.fused_output_proj and not torch.is_grad_enabled() and (not self.training or self.dropout.p == 0.0)
+                and ops.value_proj_supported(lin.in_features, lin.out_features, attended.dtype)):
+            # output_proj + residual in one tcgen05 kernel; the residual must have the (bs, n, E) memory order
+            res = residual if self.batch_first else residual.transpose(0, 1)
+            if res.is_contiguous() and res.dtype == attended.dtype:
+                out = ops.output_proj(attended, lin.weight, lin.bias, res)
+                return out if self.batch_first else out.transpose(0, 1)
+        out = lin(attended)
         if not self.batch_first:
             out = out.transpose(0, 1)
         return self.dropout(out) + residual

@@ -329,6 +329,32 @@ def value_proj(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None, key_pad
     return out if num_heads is None else out.view(bs, keys, num_heads, fout // num_heads)
 
 
+def output_proj(attended: Tensor, weight: Tensor, bias: Optional[Tensor], residual: Tensor) -> Tensor:
+    """Consumer of the op's output in one tcgen05 kernel: ``linear(attended, weight, bias) + residual``
+    (/root/reference/codetr/multi_scale_deformable_attention.py:212-218 with dropout in inference mode).
+
+    ``attended [bs, Q, in]`` (the op's output), ``weight [out, in]``, ``bias [out]`` or None, ``residual [bs, Q, out]``.
+    Same shape / dtype limits as :func:`value_proj`; raises outside them."""
+    _require(attended.is_cuda and weight.is_cuda and residual.is_cuda and attended.device == weight.device == residual.device,
+             "output_proj needs CUDA tensors on one device")
+    _require(attended.dim() == 3 and weight.dim() == 2 and weight.shape[1] == attended.shape[-1], "bad attended / weight shapes")
+    _require(attended.is_contiguous() and weight.is_contiguous() and residual.is_contiguous(), "tensors have to be contiguous")
+    _require(attended.dtype == weight.dtype == residual.dtype, "dtypes differ")
+    bs, queries, fin = attended.shape
+    fout = weight.shape[0]
+    _require(tuple(residual.shape) == (bs, queries, fout), "residual shape mismatch")
+    _require(value_proj_supported(fin, fout, attended.dtype), f"no projection kernel for {fin} -> {fout} in {attended.dtype}")
+    if bias is not None:
+        _require(bias.is_cuda and bias.is_contiguous() and bias.dtype == attended.dtype and tuple(bias.shape) == (fout,), "bad bias")
+    out = torch.empty_like(residual)
+    with torch.cuda.device(attended.device):
+        rc = _lib.msda_b200_output_proj(attended.data_ptr(), weight.data_ptr(), 0 if bias is None else bias.data_ptr(),
+                                        residual.data_ptr(), out.data_ptr(), bs * queries, fin, fout, _DTYPES[attended.dtype], 0,
+                                        _stream_ptr(attended.device, None))
+    _check(rc)
+    return out
+
+
 def plugin_enqueue(
     value_dims: Sequence[int],
     loc_dims: Sequence[int],

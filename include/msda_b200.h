@@ -236,6 +236,16 @@ uint64_t msda_b200_algorithmic_gather_bytes(int64_t batch, int64_t num_heads, in
  * MSDA_ERR_UNSUPPORTED and the caller keeps its own GEMM.  Same conventions as the other entry points: no
  * allocation, no synchronisation, launches only on `stream`, capture-safe. */
 int msda_b200_value_proj_supported(int64_t in_features, int64_t out_features, int dtype);
+/* The consumer of the op's output, same kernel with a residual epilogue: output_proj + (inference-mode) dropout +
+ * residual of the calling module (/root/reference/codetr/multi_scale_deformable_attention.py:212-218):
+ *
+ *     out[r, :] = round(attended[r, :] @ weight^T + bias) + residual[r, :]
+ *
+ * (the Linear result is rounded to the element type before the residual is added, like the two PyTorch ops it
+ * replaces).  attended [rows, in_features] = the [B, Q, M*D] output of msda_b200_forward, residual and out
+ * [rows, out_features]; `out` may alias `residual`.  Same shape / dtype limits as msda_b200_value_proj. */
+int msda_b200_output_proj(const void *attended, const void *weight, const void *bias, const void *residual, void *out,
+                          int64_t rows, int64_t in_features, int64_t out_features, int dtype, unsigned flags, void *stream);
 int msda_b200_value_proj(const void *x, const void *weight, const void *bias, const unsigned char *key_padding_mask,
                          void *value, int64_t rows, int64_t in_features, int64_t out_features, int dtype, unsigned flags,
                          void *stream);

@@ -6,6 +6,8 @@ residual) at the BASELINE shapes, with CUDA events over back-to-back forwards:
 
   unfused      producers as separate PyTorch ops + this repo's op (what the unchanged reference module does)
   fused        ``fused_producers=True``: softmax + locations inside the kernel (``msda_b200_forward_fused``)
+  fused_all    + ``fused_value_proj=True``: value_proj + masked_fill in the tcgen05 kernel (``msda_b200_value_proj``)
+  *_graphed    the same forwards captured in a CUDA graph: device time without the eager-mode host overhead
   reference    the same module with the reference's own CUDA kernel (oracle/_ref, rebuilt for sm_100a) as the op
   op only      this repo's op alone on the tensors the module feeds it
 
@@ -40,6 +42,33 @@ def time_fn(fn, iters, warmup=10):
         e.record()
         torch.cuda.synchronize()
         us = 1e3 * s.elapsed_time(e) / iters
+        best = us if best is None else min(best, us)
+    return best
+
+
+def time_graphed(fn, copies=4, replays=10):
+    """Device time per forward with the host out of the picture (what an engine runtime sees)."""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        fn()
+        side.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            for _ in range(copies):
+                fn()
+    for _ in range(2):
+        g.replay()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    best = None
+    for _ in range(3):
+        s.record()
+        for _ in range(replays):
+            g.replay()
+        e.record()
+        torch.cuda.synchronize()
+        us = 1e3 * s.elapsed_time(e) / (replays * copies)
         best = us if best is None else min(best, us)
     return best
 
@@ -88,6 +117,15 @@ def main():
                    "fused_vs_unfused_max_rel": float((out_fused.float() - out_unfused.float()).abs().max() / scale),
                    "unfused_us": time_fn(lambda: mods[False](query, **kw), iters),
                    "fused_us": time_fn(lambda: mods[True](query, **kw), iters)}
+            if dt != torch.float32:  # + the tensor-core value producer (Linear + masked_fill in one kernel)
+                mods[True].fused_value_proj = True
+                out_all = mods[True](query, **kw)
+                row["fused_all_vs_unfused_max_rel"] = float((out_all.float() - out_unfused.float()).abs().max() / scale)
+                row["fused_all_us"] = time_fn(lambda: mods[True](query, **kw), iters)
+                row["fused_all_graphed_us"] = time_graphed(lambda: mods[True](query, **kw))
+                mods[True].fused_value_proj = False
+            row["unfused_graphed_us"] = time_graphed(lambda: mods[False](query, **kw))
+            row["fused_graphed_us"] = time_graphed(lambda: mods[True](query, **kw))
             # the op alone, on what the module feeds it
             m = mods[False]
             keys = m._keys(feats, mask).contiguous()

@@ -120,6 +120,31 @@ def test_value_proj_under_cuda_graph_and_side_stream(cuda_device):
 
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("bs,queries,fin,fout", [(1, 1, 256, 256), (2, 129, 256, 256), (1, 18414, 256, 256), (3, 500, 128, 256), (1, 900, 256, 64)])
+def test_output_proj_matches_linear_plus_residual(bs, queries, fin, fout, dtype, cuda_device):
+    """``msda_b200_output_proj``: Linear rounded to 16 bits, then + residual, rounded again -- the same two roundings
+    as ``output_proj(x) + identity`` in PyTorch, so the two agree to one unit of the last place of the sum."""
+    x, w, b, _ = _case(cuda_device, dtype, bs, queries, fin, fout, seed=queries + fout)
+    res = torch.randn(bs, queries, fout, device=cuda_device).to(dtype)
+    out = cb.output_proj(x, w, b, res)
+    torch.cuda.synchronize()
+    assert cb.last_variant().startswith("output_proj<") and out.shape == res.shape and out.dtype == dtype
+    lib = F.linear(x, w, b) + res
+    ref = F.linear(x.float(), w.float(), b.float()).to(dtype).float() + res.float()
+    err = (out.float() - ref).abs()
+    assert float((err - (2.0 * ULP[dtype] * (ref.abs() + F.linear(x.float(), w.float(), b.float()).abs()) + 1e-5)).max()) <= 0.0
+    assert float((out.float() - lib.float()).abs().max()) <= float(4.0 * ULP[dtype] * lib.float().abs().max() + 1e-6)
+    # in place on the residual (the module's identity buffer may be reused)
+    res2 = res.clone()
+    lib_ = cb._native.load()
+    rc = lib_.msda_b200_output_proj(x.data_ptr(), w.data_ptr(), b.data_ptr(), res2.data_ptr(), res2.data_ptr(), bs * queries, fin, fout,
+                                    cb.ops._DTYPES[dtype], 0, torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert torch.equal(res2, out)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
 def test_module_with_fused_value_proj(dtype, cuda_device):
     """``fused_value_proj=True`` swaps the module's Linear + masked_fill for the kernel; the layer output must
     agree with the unfused layer to 16-bit rounding."""
@@ -132,7 +157,7 @@ def test_module_with_fused_value_proj(dtype, cuda_device):
         mod.sampling_offsets.weight.normal_(0, 0.02)
         mod.value_proj.bias.normal_(0, 0.1)
     mod.eval()
-    query, value, ref, shapes, lsi, mask = _inputs(cuda_device, dtype, None)
+    query, value, ref, shapes, lsi, mask = _inputs(cuda_device, dtype, None, bs=1)  # (n, 1, E): both memory orders coincide
     kw = dict(value=value, key_padding_mask=mask, reference_points=ref, spatial_shapes=shapes, level_start_index=lsi)
     with torch.no_grad():
         a = mod(query, **kw)
@@ -140,5 +165,12 @@ def test_module_with_fused_value_proj(dtype, cuda_device):
         mod.fused_value_proj = True
         b = mod(query, **kw)
         assert cb.launch_count() == launches + 2  # value_proj + the sampling kernel
-    err = float((a.float() - b.float()).abs().max() / a.float().abs().max())
-    assert err < (4e-3 if dtype == torch.float16 else 2e-2), err
+        mod.fused_output_proj = True
+        c = mod(query, **kw)
+        assert cb.launch_count() == launches + 5 and cb.last_variant().startswith("output_proj<")
+        mod.fused_producers = True
+        d = mod(query, **kw)
+    assert c.shape == a.shape and d.shape == a.shape
+    for other in (b, c, d):
+        err = float((a.float() - other.float()).abs().max() / a.float().abs().max())
+        assert err < (4e-3 if dtype == torch.float16 else 2e-2), err
