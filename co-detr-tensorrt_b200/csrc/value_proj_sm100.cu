@@ -141,6 +141,15 @@ __device__ __forceinline__ void tmem_load_32_async(uint32_t taddr, uint32_t (&v)
       : "memory");
 }
 
+// (a, b) = (x0 + y0, x1 + y1), one packed fp32 instruction; each half is an ordinary round-to-nearest add
+__device__ __forceinline__ void add2(float &a, float &b, float x0, float x1, float y0, float y1) {
+  unsigned long long x, y, r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(x0), "f"(x1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(y) : "f"(y0), "f"(y1));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(x), "l"(y));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(r));
+}
+
 template <bool BF16>
 __device__ __forceinline__ float elem_to_float(unsigned short bits) {
   if constexpr (BF16) return __uint_as_float((unsigned)bits << 16);
@@ -328,7 +337,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 
 // Dynamic shared memory (1024-byte aligned): weight chunks (K/64 x N x 128 B), x ring (kStages x 16 KB), output
 // staging (kStageChunks x 16 KB), bias as fp32 [N], barriers, TMEM base address.
-template <bool BF16>
+template <bool BF16, bool RESIDUAL>
 __global__ void __launch_bounds__(kPersistentThreads, 1)
 value_proj_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                              const __grid_constant__ CUtensorMap map_out, const ProjParams p, int pdl) {
@@ -474,8 +483,10 @@ value_proj_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __
       const int buf = t & 1;
       const int r = tile * kTileRows + rl;
       const bool padded = p.mask != nullptr && r < p.rows && p.mask[r] != 0;
-      const unsigned char *res_row =
-          (p.residual != nullptr && r < p.rows) ? static_cast<const unsigned char *>(p.residual) + (size_t)r * p.N * 2 : nullptr;
+      const unsigned char *res_row = nullptr;  // RESIDUAL: this thread's row of the tensor added after the bias
+      if constexpr (RESIDUAL) {
+        if (r < p.rows) res_row = static_cast<const unsigned char *>(p.residual) + (size_t)r * p.N * 2;
+      }
       mbar_wait(&acc_full[buf], ((unsigned)t >> 1) & 1u);
       if (t == 0 && threadIdx.x == 0) VPROJ_TRACE(5);  // first accumulator complete
       if (t == 0 && threadIdx.x == 0) VPROJ_TRACE_EPI(0);
@@ -498,32 +509,40 @@ value_proj_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         __syncwarp();
         if (tr) VPROJ_TRACE_EPI(2);
+        // the chunk's 64 bias values, loaded before the first slab store: the compiler cannot prove that the
+        // slab stores do not alias the bias array, so loads left inside the loop are serialised behind them
+        float4 bias_r[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) bias_r[i] = *reinterpret_cast<const float4 *>(bias_f + oc * 64 + i * 4);
         auto emit = [&](const uint32_t(&cur)[32], int g) {  // g: which 32-column half of the chunk
 #pragma unroll
           for (int i = 0; i < 4; ++i) {  // four 16-byte pieces = 8 elements each
-            const float4 b0 = *reinterpret_cast<const float4 *>(bias_f + oc * 64 + g * 32 + i * 8);
-            const float4 b1 = *reinterpret_cast<const float4 *>(bias_f + oc * 64 + g * 32 + i * 8 + 4);
+            const int piece = g * 4 + i;
+            uint4 *dst = reinterpret_cast<uint4 *>(slab_row + ((piece ^ (lane & 7)) << 4));
+            const float4 b0 = bias_r[g * 8 + i * 2], b1 = bias_r[g * 8 + i * 2 + 1];
             const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
             uint4 res = make_uint4(0u, 0u, 0u, 0u);
-            if (res_row != nullptr) res = __ldg(reinterpret_cast<const uint4 *>(res_row + (size_t)(oc * 64 + g * 32 + i * 8) * 2));
+            if constexpr (RESIDUAL) {
+              if (res_row != nullptr) res = __ldg(reinterpret_cast<const uint4 *>(res_row + (size_t)(oc * 64 + g * 32 + i * 8) * 2));
+            }
             const unsigned rw[4] = {res.x, res.y, res.z, res.w};
             uint4 o;
             unsigned *ow = reinterpret_cast<unsigned *>(&o);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              // Linear output rounded to the element type first, then the residual added and rounded again: the
-              // same two roundings as output_proj followed by a separate add in 16 bits
-              float a = padded ? 0.f : __uint_as_float(cur[i * 8 + j * 2]) + bb[j * 2];
-              float b = padded ? 0.f : __uint_as_float(cur[i * 8 + j * 2 + 1]) + bb[j * 2 + 1];
-              if (res_row != nullptr) {
+              // accumulator + bias in fp32, two columns per instruction (add.f32x2 -> SASS FADD2)
+              float a, b;
+              add2(a, b, __uint_as_float(cur[i * 8 + j * 2]), __uint_as_float(cur[i * 8 + j * 2 + 1]), bb[j * 2], bb[j * 2 + 1]);
+              if constexpr (RESIDUAL) {
+                // Linear output rounded to the element type first, then the residual added and rounded again: the
+                // same two roundings as output_proj followed by a separate add in 16 bits
                 const unsigned lin = pack_pair<BF16>(a, b);
                 a = elem_to_float<BF16>((unsigned short)(lin & 0xffffu)) + elem_to_float<BF16>((unsigned short)(rw[j] & 0xffffu));
                 b = elem_to_float<BF16>((unsigned short)(lin >> 16)) + elem_to_float<BF16>((unsigned short)(rw[j] >> 16));
               }
-              ow[j] = pack_pair<BF16>(a, b);
+              ow[j] = padded ? 0u : pack_pair<BF16>(a, b);  // a padded key: zeros whatever the GEMM produced
             }
-            const int piece = g * 4 + i;
-            *reinterpret_cast<uint4 *>(slab_row + ((piece ^ (lane & 7)) << 4)) = o;
+            *dst = o;  // no branch in this loop: the 16 bias loads of a chunk are all issued up front
           }
         };
         emit(v0, 0);
@@ -649,7 +668,7 @@ static int launch_projection(const void *x, const void *weight, const void *bias
   }
   const unsigned tiles = (unsigned)((rows + kTileRows - 1) / kTileRows);
   // opt in to > 48 KB of dynamic shared memory once per (device, kernel)
-  static std::atomic<int> attr_set[64][4];
+  static std::atomic<int> attr_set[64][6];
   auto opt_in = [&](const void *fn, int slot, size_t bytes) -> cudaError_t {
     if (attr_set[dev][slot].load(std::memory_order_acquire)) return cudaSuccess;
     const cudaError_t ae = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
@@ -666,8 +685,10 @@ static int launch_projection(const void *x, const void *weight, const void *bias
     msda_detail::set_last_variant(bf16 ? "value_proj<bf16>/tcgen05/single-tile" : "value_proj<f16>/tcgen05/single-tile");
   } else {
     const size_t smem = persistent_smem_bytes(K, N) + 1024;
-    auto kernel = bf16 ? value_proj_persistent_kernel<true> : value_proj_persistent_kernel<false>;
-    const cudaError_t ae = opt_in(reinterpret_cast<const void *>(kernel), bf16 ? 3 : 2, persistent_smem_bytes(kMaxChunks * kChunkK, kMaxN) + 1024);
+    auto kernel = residual ? (bf16 ? value_proj_persistent_kernel<true, true> : value_proj_persistent_kernel<false, true>)
+                           : (bf16 ? value_proj_persistent_kernel<true, false> : value_proj_persistent_kernel<false, false>);
+    const cudaError_t ae = opt_in(reinterpret_cast<const void *>(kernel), 2 + (bf16 ? 1 : 0) + (residual ? 2 : 0),
+                                  persistent_smem_bytes(kMaxChunks * kChunkK, kMaxN) + 1024);
     if (ae != cudaSuccess) return (int)ae;
     const unsigned grid = tiles < (unsigned)sms ? tiles : (unsigned)sms;
     // programmatic dependent launch: this kernel's set-up overlaps the tail of the previous kernel of the

@@ -6,7 +6,8 @@ residual) at the BASELINE shapes, with CUDA events over back-to-back forwards:
 
   unfused      producers as separate PyTorch ops + this repo's op (what the unchanged reference module does)
   fused        ``fused_producers=True``: softmax + locations inside the kernel (``msda_b200_forward_fused``)
-  fused_all    + ``fused_value_proj=True``: value_proj + masked_fill in the tcgen05 kernel (``msda_b200_value_proj``)
+  fused_all    + ``fused_value_proj`` / ``fused_output_proj``: value_proj + masked_fill and output_proj + residual in the
+               tcgen05 projection kernel (``msda_b200_value_proj`` / ``msda_b200_output_proj``)
   *_graphed    the same forwards captured in a CUDA graph: device time without the eager-mode host overhead
   reference    the same module with the reference's own CUDA kernel (oracle/_ref, rebuilt for sm_100a) as the op
   op only      this repo's op alone on the tensors the module feeds it
@@ -118,12 +119,12 @@ def main():
                    "unfused_us": time_fn(lambda: mods[False](query, **kw), iters),
                    "fused_us": time_fn(lambda: mods[True](query, **kw), iters)}
             if dt != torch.float32:  # + the tensor-core value producer (Linear + masked_fill in one kernel)
-                mods[True].fused_value_proj = True
+                mods[True].fused_value_proj = mods[True].fused_output_proj = True
                 out_all = mods[True](query, **kw)
                 row["fused_all_vs_unfused_max_rel"] = float((out_all.float() - out_unfused.float()).abs().max() / scale)
                 row["fused_all_us"] = time_fn(lambda: mods[True](query, **kw), iters)
                 row["fused_all_graphed_us"] = time_graphed(lambda: mods[True](query, **kw))
-                mods[True].fused_value_proj = False
+                mods[True].fused_value_proj = mods[True].fused_output_proj = False
             row["unfused_graphed_us"] = time_graphed(lambda: mods[False](query, **kw))
             row["fused_graphed_us"] = time_graphed(lambda: mods[True](query, **kw))
             # the op alone, on what the module feeds it

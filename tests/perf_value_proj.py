@@ -107,10 +107,18 @@ def main():
             os.environ["MSDA_B200_VPROJ_SINGLE_TILE"] = "1"
             g_single = time_graphed(ours)
             os.environ.pop("MSDA_B200_VPROJ_SINGLE_TILE")
+        # the consumer side: output_proj + residual (same kernel, residual epilogue) vs Linear followed by an add
+        res = [torch.randn(batch, wl.S, N, device=dev).to(dt) for _ in range(n_sets)]
+        ours_o = [(lambda x=x, r=r: cb.output_proj(x, w, b, r)) for x, r in zip(xs, res)]
+        lib_o = [(lambda x=x, r=r: F.linear(x, w, b) + r) for x, r in zip(xs, res)]
+        with torch.inference_mode():
+            g_out, g_out_lib = time_graphed(ours_o), time_graphed(lib_o)
         hbm = rows * (K + N) * 2 + N * K * 2 + rows
         row = {"workload": name, "batch": batch, "dtype": dtn, "rows": rows, "K": K, "N": N, "n_sets": n_sets,
                "value_proj_us": t_ours, "linear_masked_fill_us": t_lib, "linear_only_us": t_gemm,
                "graphed_value_proj_us": g_ours, "graphed_single_tile_variant_us": g_single, "graphed_linear_masked_fill_us": g_lib, "graphed_linear_only_us": g_gemm,
+               "graphed_output_proj_us": g_out, "graphed_linear_add_us": g_out_lib,
+               "output_proj_hbm_GBps": (rows * (K + 2 * N) * 2 + N * K * 2) / g_out / 1e3,
                "hbm_GBps": hbm / g_ours / 1e3, "tflops": 2.0 * rows * K * N / g_ours / 1e6,
                "max_rel_vs_cublas_path": err}
         rows_out.append(row)

@@ -25,11 +25,13 @@ assert lib.msda_b200_debug_vproj_trace(buf.ctypes.data, ctas) == 0
 t = buf.astype(np.int64)
 t0 = t[:, 0].min()
 if os.environ.get("VPROJ_TRACE_EPI"):
-    names = ["acc ready", "tmem ld done (pass 0)", "staging free barrier", "staging written+fence", "written barrier", "tma store issued",
-             "tma read done", "tile 0 epilogue done"]
+    names = ["acc ready", "tmem ld done (chunk 0)", "slab free (prev store read)", "slab written + fence", "tma store issued", None, None,
+             "tile 0 epilogue done"]
 else:
     names = ["entry", "setup done", "weights landed", "first x chunk", "tile0 MMAs issued", "tile0 acc ready", "tile0 stored", "exit"]
 print(f"rows={rows} ctas={ctas}  (ns after the first CTA's entry; median / min / max over CTAs)")
 for i, n in enumerate(names):
+    if n is None:
+        continue
     d = t[:, i] - t0
     print(f"  {n:20s} {int(np.median(d)):7d} {int(d.min()):7d} {int(d.max()):7d}")
