@@ -60,6 +60,7 @@ def parse_args():
     ap.add_argument("--cuda-graph", action="store_true", help="replay the K steps from one captured CUDA graph")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the bounded CPU sample")
     ap.add_argument("--no-batch-sweep", action="store_true", help="skip the extra per-GPU batch 2/4/8 rows (N=1 only)")
+    ap.add_argument("--no-neighbours", action="store_true", help="skip the extra row for the value_proj tcgen05 kernel (N=1 only)")
     return ap.parse_args()
 
 
@@ -255,6 +256,62 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------------
 # the B200 arm
 # --------------------------------------------------------------------------------------------
+def time_value_proj(dev, dt, bsz, keys, embed, heads):
+    """Device time of msda_b200_value_proj (rows = bsz * keys, K = N = embed) inside a CUDA graph, inputs rotated
+    over > L2 worth of buffers, next to what the reference module runs for the same lines (cuBLAS Linear +
+    masked_fill).  Roofline against HBM: algorithmic bytes = rows*(K+N)*2 + N*K*2 + rows."""
+    import torch
+    import torch.nn.functional as F
+
+    import codetr_b200 as cb
+
+    rows = bsz * keys
+    n_sets = min(32, max(2, -(-int(1.5 * L2_BYTES) // (rows * 2 * embed * 2))))
+    torch.manual_seed(0)
+    w = (torch.randn(embed, embed, device=dev) / embed ** 0.5).to(dt)
+    b = torch.randn(embed, device=dev).to(dt)
+    xs = [torch.randn(bsz, keys, embed, device=dev).to(dt) for _ in range(n_sets)]
+    mask = torch.zeros(bsz, keys, dtype=torch.bool, device=dev)
+    mask[:, -keys // 10:] = True
+
+    def graphed(fns):
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side), torch.inference_mode():
+            for f in fns:
+                f()
+            side.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                for f in fns:
+                    f()
+        for _ in range(3):
+            g.replay()
+        torch.cuda.synchronize()
+        s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        best = None
+        for _ in range(3):
+            s_ev.record()
+            for _ in range(20):
+                g.replay()
+            e_ev.record()
+            torch.cuda.synchronize()
+            us = 1e3 * s_ev.elapsed_time(e_ev) / (20 * len(fns))
+            best = us if best is None else min(best, us)
+        return best
+
+    ours = graphed([(lambda x=x: cb.value_proj(x, w, b, mask, num_heads=heads)) for x in xs])
+    variant = cb.last_variant()
+    lib = graphed([(lambda x=x: F.linear(x, w, b).masked_fill(mask[..., None], 0.0)) for x in xs])
+    hbm = rows * 2 * embed * 2 + embed * embed * 2 + rows
+    peak, peak_src = measured_peaks()
+    return {"kernel": variant, "rows": rows, "K": embed, "N": embed, "us_per_call": ours, "cublas_linear_masked_fill_us": lib,
+            "roofline": {"bound": "hbm", "achieved": hbm / ours / 1e3, "peak": peak, "unit": "GB/s", "frac": hbm / ours / 1e3 / peak,
+                         "algorithmic_bytes_per_launch": hbm, "peak_source": peak_src},
+            "tflops": 2.0 * rows * embed * embed / ours / 1e6,
+            "timing": f"CUDA graph of {n_sets} calls on rotating inputs (> L2), device time per call"}
+
+
 def run_b200(args):
     import numpy as np
     import torch
@@ -466,6 +523,14 @@ def run_b200(args):
             del sets_b
             torch.cuda.empty_cache()
 
+    # ---- extra row (N=1, 16-bit only): the producer of `value` (Linear + masked_fill, tcgen05 kernel) ----
+    neighbours = None
+    if world == 1 and not args.no_neighbours and esize == 2:
+        neighbours = {}
+        embed = wl.num_heads * wl.channels
+        for bsz in (batch, 4 * batch):
+            neighbours[f"value_proj_b{bsz}"] = time_value_proj(dev, dt, bsz, wl.S, embed, wl.num_heads)
+
     if use_dist:
         dist.destroy_process_group()
     if rank != 0:
@@ -513,7 +578,7 @@ def run_b200(args):
                       "plugin": "msda_b200_plugin_enqueue (TensorRT enqueue convention), back to back on one stream",
                       "torch_op": "torch.ops.codetr.multi_scale_deformable_attention, back to back"}[args.api],
         },
-        "roofline": roofline, "roofline_l2_gather": roofline_l2, "batch_sweep": batch_sweep, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+        "roofline": roofline, "roofline_l2_gather": roofline_l2, "batch_sweep": batch_sweep, "neighbour_kernels": neighbours, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
         "clocks": sampler.summary(),
     }
 
