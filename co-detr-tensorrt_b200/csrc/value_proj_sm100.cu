@@ -84,6 +84,25 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, i
                "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
                : "memory");
 }
+// the same load delivered to the same shared-memory offset (and mbarrier) of every CTA of the cluster named in `mask`
+__device__ __forceinline__ void tma_load_2d_multicast(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar,
+                                                      unsigned short mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ unsigned cluster_cta_rank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, const void *src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(smem_u32(src)),
                "r"(c0), "r"(c1)
@@ -340,7 +359,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 template <bool BF16, bool RESIDUAL>
 __global__ void __launch_bounds__(kPersistentThreads, 1)
 value_proj_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
-                             const __grid_constant__ CUtensorMap map_out, const ProjParams p, int pdl) {
+                             const __grid_constant__ CUtensorMap map_out, const ProjParams p, int pdl, int cluster) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int chunks = p.K / kChunkK;
@@ -392,12 +411,12 @@ value_proj_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       // first tile + weights, chunk by chunk, before the rest of the CTA has finished its set-up
       if (pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
-      if ((int)blockIdx.x < tiles) {
-        for (int c = 0; c < chunks; ++c) {
-          load_x_chunk((int)blockIdx.x, c);
-          mbar_expect_tx(&w_full[c], (unsigned)(p.N * 128));
-          tma_load_2d(w_tile + (size_t)c * p.N * 128, &map_w, c * kChunkK, 0, &w_full[c]);
-        }
+      // cluster > 1: the weights arrive as multicast slices issued by every CTA of the cluster after the cluster-wide
+      // barrier below (map_w's box is then N / cluster rows); every CTA expects the whole matrix on its own barriers
+      for (int c = 0; c < chunks; ++c) {
+        if ((int)blockIdx.x < tiles) load_x_chunk((int)blockIdx.x, c);
+        mbar_expect_tx(&w_full[c], (unsigned)(p.N * 128));
+        if (cluster == 1) tma_load_2d(w_tile + (size_t)c * p.N * 128, &map_w, c * kChunkK, 0, &w_full[c]);
       }
     }
     __syncwarp();
@@ -413,9 +432,21 @@ value_proj_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (cluster > 1) cluster_sync_all();  // every CTA's barriers exist before anybody multicasts into them
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) VPROJ_TRACE(1);  // set-up done (barriers, TMEM, bias)
+  if (cluster > 1 && warp == kProducerWarp && lane == 0) {
+    // this CTA's slice of every weight chunk, delivered to all CTAs of the cluster: one L2 read per cluster instead
+    // of one per SM (148 SMs pulling the same 128 KB is what bounds the first tile)
+    const int slice_rows = p.N / cluster;
+    const int rank = (int)cluster_cta_rank();
+    const unsigned short mask = (unsigned short)((1u << cluster) - 1u);
+    for (int c = 0; c < chunks; ++c) {
+      tma_load_2d_multicast(w_tile + (size_t)c * p.N * 128 + (size_t)rank * slice_rows * 128, &map_w, c * kChunkK, rank * slice_rows,
+                            &w_full[c], mask);
+    }
+  }
   // let the next kernel of the stream start its own launch / set-up (it waits for our memory in its own
   // griddepcontrol.wait; kernels launched without the attribute are unaffected)
   if (pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -464,6 +495,9 @@ value_proj_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __
         }
         umma_commit(&acc_full[buf]);
         if (t == 0) VPROJ_TRACE(4);  // first tile's MMAs issued
+      }
+      if (t == 0) {  // a CTA without tiles still receives the cluster's weight multicasts: let them land before exit
+        for (int c = 0; c < chunks; ++c) mbar_wait(&w_full[c], 0);
       }
     }
     __syncwarp();
@@ -568,6 +602,7 @@ value_proj_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __
   if (warp == kMmaWarp) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }
+  if (cluster > 1) cluster_sync_all();  // nobody leaves while a peer could still be reading or writing its shared memory
   if (threadIdx.x == 0) VPROJ_TRACE(7);  // exit
 }
 
@@ -690,7 +725,21 @@ static int launch_projection(const void *x, const void *weight, const void *bias
     const cudaError_t ae = opt_in(reinterpret_cast<const void *>(kernel), 2 + (bf16 ? 1 : 0) + (residual ? 2 : 0),
                                   persistent_smem_bytes(kMaxChunks * kChunkK, kMaxN) + 1024);
     if (ae != cudaSuccess) return (int)ae;
-    const unsigned grid = tiles < (unsigned)sms ? tiles : (unsigned)sms;
+    // thread-block clusters (opt-in, MSDA_B200_VPROJ_CLUSTER = 2 or 4): the CTAs of a cluster share one L2 read of the
+    // weight matrix through TMA multicast.  Measured slower than every CTA loading its own copy (6.5 -> 8.2 us with
+    // pairs, 14.0 us with clusters of 4 at the headline shape: the two cluster-wide barriers and the later start of the
+    // weight loads cost more than the 9.5 MB of L2 reads they save), so the default is 1.
+    int cluster = 1;
+    if (const char *ce = getenv("MSDA_B200_VPROJ_CLUSTER")) cluster = atoi(ce);
+    if (cluster != 1 && cluster != 2 && cluster != 4) cluster = 1;
+    if ((N / cluster) % 8 != 0 || N / cluster > 256) cluster = 1;
+    if (cluster > 1 && !make_map(&map_w, weight, bf16, (uint64_t)K, (uint64_t)N, (uint32_t)(N / cluster))) return MSDA_ERR_UNSUPPORTED;
+    unsigned grid = tiles < (unsigned)sms ? tiles : (unsigned)sms;
+    if (cluster > 1) {
+      grid = (grid + cluster - 1) / cluster * cluster;            // whole clusters; surplus CTAs only relay weights
+      const unsigned fit = (unsigned)sms / cluster * cluster;
+      if (grid > fit) grid = fit;
+    }
     // programmatic dependent launch: this kernel's set-up overlaps the tail of the previous kernel of the
     // stream, and it releases its own dependents right after set-up (MSDA_B200_PDL=0 launches the plain way)
     const char *pdl_env = getenv("MSDA_B200_PDL");
@@ -701,15 +750,27 @@ static int launch_projection(const void *x, const void *weight, const void *bias
     cfg.blockDim = dim3(kPersistentThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attr[2];
+    unsigned n_attr = 0;
+    if (pdl) {
+      attr[n_attr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[n_attr].val.programmaticStreamSerializationAllowed = 1;
+      ++n_attr;
+    }
+    if (cluster > 1) {
+      attr[n_attr].id = cudaLaunchAttributeClusterDimension;
+      attr[n_attr].val.clusterDim.x = (unsigned)cluster;
+      attr[n_attr].val.clusterDim.y = 1;
+      attr[n_attr].val.clusterDim.z = 1;
+      ++n_attr;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = pdl ? 1 : 0;
-    const cudaError_t le = cudaLaunchKernelEx(&cfg, kernel, map_x, map_w, map_out, p, pdl);
+    cfg.numAttrs = n_attr;
+    const cudaError_t le = cudaLaunchKernelEx(&cfg, kernel, map_x, map_w, map_out, p, pdl, cluster);
     if (le != cudaSuccess) return (int)le;
-    if (residual) msda_detail::set_last_variant(bf16 ? "output_proj<bf16>/tcgen05/persistent" : "output_proj<f16>/tcgen05/persistent");
-    else msda_detail::set_last_variant(bf16 ? "value_proj<bf16>/tcgen05/persistent" : "value_proj<f16>/tcgen05/persistent");
+    char name[96];
+    snprintf(name, sizeof(name), "%s<%s>/tcgen05/cluster%d/persistent", residual ? "output_proj" : "value_proj", bf16 ? "bf16" : "f16", cluster);
+    msda_detail::set_last_variant(name);
   }
   msda_detail::launch_count.fetch_add(1, std::memory_order_relaxed);
   return (int)cudaGetLastError();

@@ -104,6 +104,11 @@ def main():
             err = float((got.float() - want.float()).abs().max() / want.float().abs().max())
             t_ours, t_lib, t_gemm = time_calls(ours, iters), time_calls(lib, iters), time_calls(gemm_only, iters)
             g_ours, g_lib, g_gemm = time_graphed(ours), time_graphed(lib), time_graphed(gemm_only)
+            g_cluster = {}
+            for c in (1, 2, 4):
+                os.environ["MSDA_B200_VPROJ_CLUSTER"] = str(c)
+                g_cluster[f"graphed_value_proj_cluster{c}_us"] = time_graphed(ours)
+            os.environ.pop("MSDA_B200_VPROJ_CLUSTER")
             os.environ["MSDA_B200_VPROJ_SINGLE_TILE"] = "1"
             g_single = time_graphed(ours)
             os.environ.pop("MSDA_B200_VPROJ_SINGLE_TILE")
@@ -116,7 +121,7 @@ def main():
         hbm = rows * (K + N) * 2 + N * K * 2 + rows
         row = {"workload": name, "batch": batch, "dtype": dtn, "rows": rows, "K": K, "N": N, "n_sets": n_sets,
                "value_proj_us": t_ours, "linear_masked_fill_us": t_lib, "linear_only_us": t_gemm,
-               "graphed_value_proj_us": g_ours, "graphed_single_tile_variant_us": g_single, "graphed_linear_masked_fill_us": g_lib, "graphed_linear_only_us": g_gemm,
+               "graphed_value_proj_us": g_ours, **g_cluster, "graphed_single_tile_variant_us": g_single, "graphed_linear_masked_fill_us": g_lib, "graphed_linear_only_us": g_gemm,
                "graphed_output_proj_us": g_out, "graphed_linear_add_us": g_out_lib,
                "output_proj_hbm_GBps": (rows * (K + 2 * N) * 2 + N * K * 2) / g_out / 1e3,
                "hbm_GBps": hbm / g_ours / 1e3, "tflops": 2.0 * rows * K * N / g_ours / 1e6,

@@ -81,6 +81,26 @@ def test_value_proj_single_tile_variant_is_bit_identical(bs, keys, cuda_device, 
         _check(a, _reference(x, w, b, m), dtype, m)
 
 
+@pytest.mark.parametrize("cluster", [1, 2, 4])
+@pytest.mark.parametrize("bs,keys", [(1, 100), (1, 7706), (2, 20000)])
+def test_value_proj_cluster_sizes_are_bit_identical(bs, keys, cluster, cuda_device, monkeypatch):
+    """Opt-in: the weight matrix reaches the CTAs of a thread-block cluster by TMA multicast (MSDA_B200_VPROJ_CLUSTER).  100 rows =
+    one tile: the other CTAs of the cluster have no tile and only relay their weight slice; 7,706 rows = 61 tiles, an
+    odd count; 40,000 rows = several tiles per CTA."""
+    for dtype in (torch.float16, torch.bfloat16):
+        x, w, b, m = _case(cuda_device, dtype, bs, keys, 256, 256, seed=keys + cluster)
+        monkeypatch.setenv("MSDA_B200_VPROJ_CLUSTER", "1")
+        want = cb.value_proj(x, w, b, m)
+        monkeypatch.setenv("MSDA_B200_VPROJ_CLUSTER", str(cluster))
+        got = cb.value_proj(x, w, b, m)
+        assert f"/cluster{cluster}/" in cb.last_variant()
+        torch.cuda.synchronize()
+        assert torch.equal(got, want)
+        _check(got, _reference(x, w, b, m), dtype, m)
+    x, w, b, m = _case(cuda_device, torch.float16, 1, 300, 128, 64, seed=3)  # narrow output: slices of 32 / 16 rows
+    assert torch.equal(cb.value_proj(x, w, b, m), F.linear(x, w, b).masked_fill(m[..., None], 0.0))
+
+
 def test_value_proj_output_is_the_ops_value_layout(cuda_device):
     x, w, b, m = _case(cuda_device, torch.float16, 2, 200, 256, 256)
     v = cb.value_proj(x, w, b, m, num_heads=8)
