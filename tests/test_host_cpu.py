@@ -83,6 +83,32 @@ def test_argument_validation_returns_before_any_cuda_work():
     assert lib.msda_b200_host_workspace_bytes(1, 16, 2, 4, 1, 3, 2, 0) >= (16 * 8 + 3 * 2 * 2 * 3 + 3 * 8) * 4
 
 
+def test_projection_entry_points_validate_before_any_cuda_work():
+    """msda_b200_value_proj / msda_b200_output_proj: what has a tensor-core kernel, and the error codes for everything
+    else, without touching the device."""
+    lib = cb._native.load()
+    sup = lib.msda_b200_value_proj_supported
+    F16, BF16, F32 = cb._native.DTYPE_F16, cb._native.DTYPE_BF16, cb._native.DTYPE_F32
+    for k, n in ((256, 256), (64, 64), (128, 256), (256, 192), (192, 64)):
+        assert sup(k, n, F16) == 1 and sup(k, n, BF16) == 1
+    assert sup(256, 256, F32) == 0 and sup(256, 256, 3) == 0                   # 16-bit element types only
+    assert sup(320, 256, F16) == 0 and sup(256, 512, F16) == 0                 # wider than the resident weight tile
+    assert sup(96, 256, F16) == 0 and sup(256, 96, F16) == 0 and sup(0, 0, F16) == 0   # not a multiple of 64
+    buf = (ctypes.c_char * 4096)()
+    p = ctypes.addressof(buf)
+    vp, op = lib.msda_b200_value_proj, lib.msda_b200_output_proj
+    assert vp(p, p, p, p, p, 10, 256, 256, 99, 0, None) == -3                   # unknown dtype
+    assert vp(p, p, p, p, p, -1, 256, 256, F16, 0, None) == -2                  # negative row count
+    assert vp(p, p, p, p, p, 10, 256, 256, F32, 0, None) == -6                  # no fp32 kernel: caller keeps its GEMM
+    assert vp(p, p, p, p, p, 10, 320, 256, F16, 0, None) == -6
+    assert vp(p, p, p, p, p, 0, 256, 256, F16, 0, None) == 0                    # no rows: nothing to launch
+    assert vp(None, p, p, p, p, 10, 256, 256, F16, 0, None) == -1               # NULL x
+    assert vp(p, p, None, None, None, 10, 256, 256, F16, 0, None) == -1         # NULL output (bias / mask may be NULL)
+    assert vp(p + 2, p, p, p, p, 10, 256, 256, F16, 0, None) == -6              # TMA needs 16-byte aligned bases
+    assert op(p, p, p, None, p, 10, 256, 256, F16, 0, None) == -1               # output_proj needs the residual
+    assert op(p, p, p, p, p, 0, 256, 256, BF16, 0, None) == 0
+
+
 def test_algorithmic_byte_counts_match_survey():
     lib = cb._native.load()
     wl = W.CONFIGS["swinl_enc_1152x768"]
