@@ -1,25 +1,30 @@
 // SPDX-License-Identifier: Apache-2.0
 //
-// value_proj_sm100.cu -- the producer of the op's `value` input for NVIDIA B200 (sm_100a):
+// value_proj_sm100.cu -- the two GEMM-shaped neighbours of the sampling kernels for NVIDIA B200 (sm_100a):
 //
-//     value[r, :] = key_padding_mask[r] ? 0 : x[r, :] @ W^T + bias          (r = image * S + key)
+//     value[r, :] = key_padding_mask[r] ? 0 : x[r, :] @ W^T + bias                 (msda_b200_value_proj)
+//     out[r, :]   = round(attended[r, :] @ W^T + bias) + residual[r, :]             (msda_b200_output_proj)
 //
-// i.e. nn.Linear + masked_fill + head split of the calling module
-// (/root/reference/codetr/multi_scale_deformable_attention.py:173-176) in ONE kernel whose output is already
-// the [B, S, M, D] tensor the sampling kernels read.  This is the one GEMM-shaped
-// neighbour of the hot path, so it runs on the 5th-generation tensor cores, hand-written:
+// i.e. nn.Linear + masked_fill + head split (/root/reference/codetr/multi_scale_deformable_attention.py:173-176)
+// and output_proj + inference-mode dropout + residual (:212-218) of the calling module, each in ONE kernel; the
+// first one's output already is the [B, S, M, D] tensor the sampling kernels read.
+// These are the only GEMMs next to the hot path, so they run on the 5th-generation tensor cores, hand-written:
 //
-//   * operands staged by TMA (cp.async.bulk.tensor.2d, 128-byte swizzle) into shared memory: the CTA's 128
-//     rows of x and the whole weight matrix (K, N <= 256), one mbarrier per 64-wide K chunk so the first MMAs
-//     start while the later chunks are still in flight;
-//   * one elected thread issues tcgen05.mma (cta_group::1, kind::f16, UMMA 128 x N x 16), fp32 accumulators
-//     in tensor memory (N columns x 128 lanes), completion signalled with tcgen05.commit on an mbarrier;
-//   * four epilogue warps read their lane quarter with tcgen05.ld (32x32b.x32), add the bias, zero the padded
-//     rows, round to the 16-bit element type and stage the tile in the (now free) x buffer in the same
-//     swizzled layout; one thread writes it back with TMA stores (out-of-range rows are clipped by the TMA).
+//   * operands staged by TMA (cp.async.bulk.tensor.2d, 128-byte swizzle) into shared memory, one mbarrier per
+//     64-wide K chunk so the first MMAs start while the later chunks are still in flight;
+//   * one elected thread issues tcgen05.mma (cta_group::1, kind::f16, UMMA 128 x N x 16), fp32 accumulators in
+//     tensor memory, completion signalled with tcgen05.commit on mbarriers;
+//   * epilogue warps read their TMEM lane quarter with tcgen05.ld (32x32b.x32), add the bias, zero the padded
+//     rows (or add the residual), round to the 16-bit element type, stage the result in 128-byte-swizzled shared
+//     memory and write it back with TMA stores (rows past the end are clipped by the TMA).
+//
+// Two kernels share those pieces: value_proj_persistent_kernel (the default: persistent CTAs, resident weights,
+// x ring, double-buffered accumulators, warp-specialised; described at its definition) and value_proj_kernel (the
+// first version, one tile per CTA, kept selectable for A/B runs).  DESIGN.md section 4.6 has the measurements.
 //
 // Nothing here allocates, synchronises or reads device memory on the host; the tensor maps are encoded per
-// call on the host (three cuTensorMapEncodeTiled calls, ~1 us) and passed as __grid_constant__ parameters.
+// call on the host (cuTensorMapEncodeTiled through cudaGetDriverEntryPoint, ~1 us) and passed as
+// __grid_constant__ parameters.
 
 #include <cuda.h>
 #include <cuda_bf16.h>
