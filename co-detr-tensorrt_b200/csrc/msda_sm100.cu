@@ -156,6 +156,7 @@ struct MsdaParams {
 
 struct LevelGeom {
   int H, W, start, qstart;
+  float rcpW, rcpH;  // correctly rounded 1/W, 1/H for the fused producers' offset normalisation
 };
 
 // ---------------------------------------------------------------------------
@@ -233,6 +234,31 @@ template <typename T>
 __device__ __forceinline__ float fused_exp(float v) {
   if constexpr (sizeof(T) == 4) return expf(v);
   else return __expf(v);
+}
+
+// a / b for fp32 with y = RN(1/b) given: one multiply and two FMAs that land on the correctly rounded quotient
+// (Markstein: q = RN(a*y), r = a - b*q exactly by FMA, RN(q + r*y) = RN(a/b)); replaces the ~10-instruction IEEE
+// division sequence in the hot loop of the fused kernel without changing a bit of the result.
+__device__ __forceinline__ float div_with_rcp(float a, float b, float rcp_b) {
+  const float q = __fmul_rn(a, rcp_b);
+  const float r = fmaf(-b, q, a);
+  return fmaf(r, rcp_b, q);
+}
+
+// the vector kernel's variant of fused_location below: fp32 arithmetic, reciprocals of W, H and P precomputed
+template <typename T>
+__device__ __forceinline__ void fused_location_fast(const T *rf, int ref_dim, float ox, float oy, float Wf, float Hf, float rcpW,
+                                                    float rcpH, float &x, float &y) {
+  if (ref_dim == 2) {
+    x = round_like<T, float>(Elem<T>::to_acc(rf[0]) + round_like<T, float>(div_with_rcp(ox, Wf, rcpW)));
+    y = round_like<T, float>(Elem<T>::to_acc(rf[1]) + round_like<T, float>(div_with_rcp(oy, Hf, rcpH)));
+  } else {
+    // P == 4 on this path: off / 4 is exact
+    const float tx = round_like<T, float>(round_like<T, float>(ox * 0.25f) * Elem<T>::to_acc(rf[2])) * 0.5f;
+    const float ty = round_like<T, float>(round_like<T, float>(oy * 0.25f) * Elem<T>::to_acc(rf[3])) * 0.5f;
+    x = round_like<T, float>(Elem<T>::to_acc(rf[0]) + tx);
+    y = round_like<T, float>(Elem<T>::to_acc(rf[1]) + ty);
+  }
 }
 
 template <typename T, typename A>
@@ -749,6 +775,8 @@ __device__ __forceinline__ void setup_tiles(const MsdaParams &p, TileSetup &ts) 
     ts.lv[l].W = W;
     ts.lv[l].start = start;
     ts.lv[l].qstart = qs - nq;
+    ts.lv[l].rcpW = __frcp_rn((float)(W > 0 ? W : 1));
+    ts.lv[l].rcpH = __frcp_rn((float)(H > 0 ? H : 1));
     ts.tile_first[l] = tsum - nt;
     ts.tiles_x[l] = tx > 0 ? tx : 1;
     ts.inv_tiles_x[l] = 1.0f / (float)(tx > 0 ? tx : 1);
@@ -1138,7 +1166,7 @@ __global__ void __launch_bounds__(kThreads, (SPLIT > 1 && P_T == 4) ? MSDA_MINB_
           if constexpr (FUSED) {
             // x, y are the raw offsets, aw the logit
             const float ox = x, oy = y;
-            fused_location<T, float>(rfp + l * p.ref_dim, p.ref_dim, ox, oy, H, W, 4, x, y);
+            fused_location_fast<T>(rfp + l * p.ref_dim, p.ref_dim, ox, oy, (float)W, (float)H, ts.lv[l].rcpW, ts.lv[l].rcpH, x, y);
             aw = round_like<T, float>(fused_exp<T>(aw - sm_max) * sm_inv);
           }
           aw = live ? aw : 0.f;
