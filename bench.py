@@ -529,7 +529,11 @@ def run_b200(args):
         neighbours = {}
         embed = wl.num_heads * wl.channels
         for bsz in (batch, 4 * batch):
-            neighbours[f"value_proj_b{bsz}"] = time_value_proj(dev, dt, bsz, wl.S, embed, wl.num_heads)
+            try:  # an extra row must never cost the headline line
+                neighbours[f"value_proj_b{bsz}"] = time_value_proj(dev, dt, bsz, wl.S, embed, wl.num_heads)
+            except Exception as exc:  # pragma: no cover
+                neighbours[f"value_proj_b{bsz}"] = {"error": f"{type(exc).__name__}: {exc}"}
+                torch.cuda.synchronize()
 
     if use_dist:
         dist.destroy_process_group()
