@@ -531,6 +531,11 @@ value_proj_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __
       if (t == 0 && threadIdx.x == 0) VPROJ_TRACE_EPI(0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t acc = tmem_base + (uint32_t)buf * acc_cols + ((uint32_t)(quarter * 32) << 16);
+      if (half >= out_chunks) {
+        // N == 64: the second warp of the quarter has no chunk, but the accumulator hand-back counts all 8 warps
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      }
       for (int oc = half; oc < out_chunks; oc += 2) {  // this warp's output chunks (64 columns each)
         const bool tr = t == 0 && threadIdx.x == 0 && oc == half;
         uint32_t v0[32], v1[32];  // named (not indexed) so they stay in registers

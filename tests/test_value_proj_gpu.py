@@ -101,6 +101,21 @@ def test_value_proj_cluster_sizes_are_bit_identical(bs, keys, cluster, cuda_devi
     assert torch.equal(cb.value_proj(x, w, b, m), F.linear(x, w, b).masked_fill(m[..., None], 0.0))
 
 
+@pytest.mark.parametrize("fin,fout", [(256, 64), (64, 64), (128, 192), (256, 128)])
+def test_value_proj_narrow_outputs_many_tiles_per_cta(fin, fout, cuda_device):
+    """60,000 rows = 469 tiles on 148 persistent CTAs: every CTA reuses both accumulator buffers.  With 64 output columns
+    half of the epilogue warps have no chunk and must still hand the accumulator back; 192 columns is the odd-chunk case."""
+    x, w, b, m = _case(cuda_device, torch.float16, 1, 60000, fin, fout, seed=fin * 3 + fout)
+    out = cb.value_proj(x, w, b, m)
+    torch.cuda.synchronize()
+    _check(out, _reference(x, w, b, m), torch.float16, m)
+    res = torch.randn(1, 60000, fout, device=cuda_device).half()
+    got = cb.output_proj(x, w, b, res)
+    torch.cuda.synchronize()
+    lib = F.linear(x, w, b) + res
+    assert float((got.float() - lib.float()).abs().max()) <= float(4.0 * ULP[torch.float16] * lib.float().abs().max() + 1e-6)
+
+
 def test_value_proj_output_is_the_ops_value_layout(cuda_device):
     x, w, b, m = _case(cuda_device, torch.float16, 2, 200, 256, 256)
     v = cb.value_proj(x, w, b, m, num_heads=8)
