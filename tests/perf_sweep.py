@@ -60,7 +60,7 @@ def time_calls(fns, iters, warmup=20):
 
 def set_env(cfg):
     for k in ("MSDA_B200_TILE_W", "MSDA_B200_TILE_H", "MSDA_B200_HEAD_MAJOR", "MSDA_B200_SPLIT", "MSDA_B200_CTAS_PER_SM",
-              "MSDA_B200_SMALL", "MSDA_B200_SPLIT_MAX_CTAS", "MSDA_B200_CHUNKED", "MSDA_B200_DYN"):
+              "MSDA_B200_SMALL", "MSDA_B200_SPLIT_MAX_CTAS", "MSDA_B200_CHUNKED", "MSDA_B200_DYN", "MSDA_B200_L2_PREFETCH"):
         os.environ.pop(k, None)
     for k, v in cfg.items():
         if k.startswith("MSDA_"):
@@ -127,6 +127,12 @@ def main():
                      ("r50_enc_608", 1, "float16", None), ("r50_enc_608", 2, "float16", None),
                      ("swinl_dec_1152x768", 8, "float16", None), ("swinl_dec_1900q", 1, "float16", None),
                      ("swinl_enc_1152x768_s4", 1, "float16", None)]
+    if args.only == "prefetch":
+        workloads = [("swinl_enc_1152x768", 1, "float16", None), ("swinl_enc_1152x768", 1, "float16", "uniform"),
+                     ("swinl_enc_1152x768", 4, "float16", None), ("swinl_enc_1152x768", 1, "bfloat16", None),
+                     ("swinl_enc_1152x768", 1, "float32", None), ("r50_enc_608", 1, "float16", None),
+                     ("swinl_dec_1152x768", 8, "float16", None), ("swinl_dec_1900q", 1, "float16", None),
+                     ("swinl_enc_1920x1280", 2, "float16", None), ("ref_test_mid_fp32", 1, "float32", None)]
     if args.only == "exact":
         workloads = [("swinl_enc_1152x768", 1, "bfloat16", None), ("swinl_enc_1152x768", 4, "bfloat16", None),
                      ("swinl_enc_1152x768", 1, "float32", None), ("swinl_enc_1152x768", 1, "float16", None),
@@ -194,6 +200,10 @@ def main():
                     {"name": "dyn ctas_per_sm4", "flags": 0, "MSDA_B200_DYN": 1, "MSDA_B200_CTAS_PER_SM": 4},
                     {"name": "dyn ctas_per_sm8", "flags": 0, "MSDA_B200_DYN": 1, "MSDA_B200_CTAS_PER_SM": 8},
                     {"name": "dyn split1", "flags": 0, "MSDA_B200_DYN": 1, "MSDA_B200_SPLIT": 1},
+                    {"name": "default again", "flags": 0}]
+            have_ref = False
+        if args.only == "prefetch":
+            cfgs = [{"name": "default", "flags": 0}, {"name": "no L2 prefetch", "flags": 0, "MSDA_B200_L2_PREFETCH": 0},
                     {"name": "default again", "flags": 0}]
             have_ref = False
         if args.only == "exact":
