@@ -53,8 +53,9 @@ constexpr int kThreads = (kEpilogueWarps + 1) * 32;  // + one producer / MMA war
 struct ProjParams {
   const void *bias;            // [N] in the element type, or nullptr
   const unsigned char *mask;   // [rows], non-zero = padded key (row of zeros), or nullptr
-  const void *residual;        // [rows, N] in the element type, added after the bias, or nullptr (output_proj mode)
-  int rows, K, N;
+  const void *residual;        // [rows, n_total] in the element type, added after the bias, or nullptr (output_proj mode)
+  int rows, K, N;              // N = output columns of ONE CTA (n_total / n_split)
+  int n_total, n_split;        // all output columns; column blocks a row tile is split into (1, 2 or 4)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -383,6 +384,10 @@ value_proj_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __
   const int warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31);
   if (threadIdx.x == 0) VPROJ_TRACE(0);  // kernel entry
   const int tiles = (p.rows + kTileRows - 1) / kTileRows;
+  // n_split > 1 (few row tiles): n_split CTAs share a row tile, each owns N = n_total / n_split output columns
+  // starting at n0 and loads only that slice of the weight matrix; the host launches exactly tiles * n_split CTAs
+  const int tile0 = (int)blockIdx.x / p.n_split, tile_step = (int)gridDim.x / p.n_split;
+  const int n0 = ((int)blockIdx.x % p.n_split) * p.N;
   const uint32_t acc_cols = p.N <= 32 ? 32u : p.N <= 64 ? 64u : p.N <= 128 ? 128u : 256u;  // per accumulator buffer
   const uint32_t tmem_cols = 2 * acc_cols;
 
@@ -419,9 +424,9 @@ value_proj_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __
       // cluster > 1: the weights arrive as multicast slices issued by every CTA of the cluster after the cluster-wide
       // barrier below (map_w's box is then N / cluster rows); every CTA expects the whole matrix on its own barriers
       for (int c = 0; c < chunks; ++c) {
-        if ((int)blockIdx.x < tiles) load_x_chunk((int)blockIdx.x, c);
+        if (tile0 < tiles) load_x_chunk(tile0, c);
         mbar_expect_tx(&w_full[c], (unsigned)(p.N * 128));
-        if (cluster == 1) tma_load_2d(w_tile + (size_t)c * p.N * 128, &map_w, c * kChunkK, 0, &w_full[c]);
+        if (cluster == 1) tma_load_2d(w_tile + (size_t)c * p.N * 128, &map_w, c * kChunkK, n0, &w_full[c]);
       }
     }
     __syncwarp();
@@ -432,7 +437,7 @@ value_proj_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __
   } else {
     if (pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
     for (int n = (int)threadIdx.x; n < p.N; n += kPEpilogueWarps * 32) {
-      bias_f[n] = p.bias ? elem_to_float<BF16>(static_cast<const unsigned short *>(p.bias)[n]) : 0.f;
+      bias_f[n] = p.bias ? elem_to_float<BF16>(static_cast<const unsigned short *>(p.bias)[n0 + n]) : 0.f;
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -459,7 +464,7 @@ value_proj_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __
   if (warp == kProducerWarp) {
     // ===== TMA producer: the remaining tiles =====
     if (lane == 0) {
-      for (int tile = (int)blockIdx.x + (int)gridDim.x; tile < tiles; tile += (int)gridDim.x) {
+      for (int tile = tile0 + tile_step; tile < tiles; tile += tile_step) {
         for (int c = 0; c < chunks; ++c) load_x_chunk(tile, c);
       }
     }
@@ -472,7 +477,7 @@ value_proj_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __
       int stage = 0;
       unsigned phase = 0;
       int t = 0;
-      for (int tile = (int)blockIdx.x; tile < tiles; tile += (int)gridDim.x, ++t) {
+      for (int tile = tile0; tile < tiles; tile += tile_step, ++t) {
         const int buf = t & 1;
         mbar_wait(&acc_empty[buf], (((unsigned)t >> 1) & 1u) ^ 1u);  // the epilogue has drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -518,13 +523,13 @@ value_proj_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __
     unsigned char *slab = staging + (size_t)warp * (32 * 128);
     unsigned char *slab_row = slab + (size_t)lane * 128;
     int t = 0;
-    for (int tile = (int)blockIdx.x; tile < tiles; tile += (int)gridDim.x, ++t) {
+    for (int tile = tile0; tile < tiles; tile += tile_step, ++t) {
       const int buf = t & 1;
       const int r = tile * kTileRows + rl;
       const bool padded = p.mask != nullptr && r < p.rows && p.mask[r] != 0;
       const unsigned char *res_row = nullptr;  // RESIDUAL: this thread's row of the tensor added after the bias
       if constexpr (RESIDUAL) {
-        if (r < p.rows) res_row = static_cast<const unsigned char *>(p.residual) + (size_t)r * p.N * 2;
+        if (r < p.rows) res_row = static_cast<const unsigned char *>(p.residual) + ((size_t)r * p.n_total + n0) * 2;
       }
       mbar_wait(&acc_full[buf], ((unsigned)t >> 1) & 1u);
       if (t == 0 && threadIdx.x == 0) VPROJ_TRACE(5);  // first accumulator complete
@@ -596,7 +601,7 @@ value_proj_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __
         __syncwarp();
         if (tr) VPROJ_TRACE_EPI(3);
         if (lane == 0) {
-          tma_store_2d(&map_out, slab, oc * kChunkK, tile * kTileRows + quarter * 32);
+          tma_store_2d(&map_out, slab, n0 + oc * kChunkK, tile * kTileRows + quarter * 32);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
         if (tr) VPROJ_TRACE_EPI(4);
@@ -703,6 +708,8 @@ static int launch_projection(const void *x, const void *weight, const void *bias
   p.rows = (int)rows;
   p.K = K;
   p.N = N;
+  p.n_total = N;
+  p.n_split = 1;
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return MSDA_ERR_UNSUPPORTED;
   static std::atomic<int> sm_count[64];
@@ -745,6 +752,23 @@ static int launch_projection(const void *x, const void *weight, const void *bias
     if ((N / cluster) % 8 != 0 || N / cluster > 256) cluster = 1;
     if (cluster > 1 && !make_map(&map_w, weight, bf16, (uint64_t)K, (uint64_t)N, (uint32_t)(N / cluster))) return MSDA_ERR_UNSUPPORTED;
     unsigned grid = tiles < (unsigned)sms ? tiles : (unsigned)sms;
+    // few row tiles (R50-sized encoders, decoder queries): split every tile's output columns over 2 or 4 CTAs so more
+    // SMs work and each ingests only its slice of the weight matrix (MSDA_B200_VPROJ_NSPLIT=1/2/4 forces it)
+    int n_split = 1;
+    if (cluster == 1) {
+      if (tiles * 4 <= (unsigned)sms && N % 256 == 0) n_split = 4;
+      else if (tiles * 2 <= (unsigned)sms && N % 128 == 0) n_split = 2;
+      if (const char *ne = getenv("MSDA_B200_VPROJ_NSPLIT")) {
+        const int forced = atoi(ne);
+        if ((forced == 1 || forced == 2 || forced == 4) && N % (64 * forced) == 0 && tiles * (unsigned)forced <= (unsigned)sms) n_split = forced;
+      }
+    }
+    if (n_split > 1) {
+      p.N = N / n_split;
+      p.n_split = n_split;
+      grid = tiles * (unsigned)n_split;
+      if (!make_map(&map_w, weight, bf16, (uint64_t)K, (uint64_t)N, (uint32_t)p.N)) return MSDA_ERR_UNSUPPORTED;
+    }
     if (cluster > 1) {
       grid = (grid + cluster - 1) / cluster * cluster;            // whole clusters; surplus CTAs only relay weights
       const unsigned fit = (unsigned)sms / cluster * cluster;
@@ -779,7 +803,8 @@ static int launch_projection(const void *x, const void *weight, const void *bias
     const cudaError_t le = cudaLaunchKernelEx(&cfg, kernel, map_x, map_w, map_out, p, pdl, cluster);
     if (le != cudaSuccess) return (int)le;
     char name[96];
-    snprintf(name, sizeof(name), "%s<%s>/tcgen05/cluster%d/persistent", residual ? "output_proj" : "value_proj", bf16 ? "bf16" : "f16", cluster);
+    snprintf(name, sizeof(name), "%s<%s>/tcgen05/cluster%d/nsplit%d/persistent", residual ? "output_proj" : "value_proj", bf16 ? "bf16" : "f16",
+             cluster, n_split);
     msda_detail::set_last_variant(name);
   }
   msda_detail::launch_count.fetch_add(1, std::memory_order_relaxed);

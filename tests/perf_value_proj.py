@@ -82,19 +82,21 @@ def main():
     rows_out = []
     for name, batch, dtn in (("swinl_enc_1152x768", 1, "float16"), ("swinl_enc_1152x768", 1, "bfloat16"),
                              ("swinl_enc_1152x768", 4, "float16"), ("r50_enc_608", 1, "float16"),
-                             ("swinl_enc_1920x1280", 2, "float16"), ("swinl_enc_1152x768_s4", 1, "float16")):
-        wl = W.CONFIGS[name]
+                             ("swinl_enc_1920x1280", 2, "float16"), ("swinl_enc_1152x768_s4", 1, "float16"),
+                             ("swinl_dec_1152x768:queries", 1, "float16")):  # 900 rows: the decoder's output_proj
+        wl = W.CONFIGS[name.split(":")[0]]
         dt = getattr(torch, dtn)
         K = N = wl.num_heads * wl.channels
-        rows = batch * wl.S
+        keys = wl.Q if name.endswith(":queries") else wl.S
+        rows = batch * keys
         per_set = rows * (K + N) * 2
         n_sets = min(32, max(2, -(-int(1.5 * L2) // per_set)))
         torch.manual_seed(0)
         w = (torch.randn(N, K, device=dev) / K ** 0.5).to(dt)
         b = torch.randn(N, device=dev).to(dt)
-        xs = [torch.randn(batch, wl.S, K, device=dev).to(dt) for _ in range(n_sets)]
-        mask = torch.zeros(batch, wl.S, dtype=torch.bool, device=dev)
-        mask[:, -wl.S // 10:] = True
+        xs = [torch.randn(batch, keys, K, device=dev).to(dt) for _ in range(n_sets)]
+        mask = torch.zeros(batch, keys, dtype=torch.bool, device=dev)
+        mask[:, -keys // 10:] = True
         ours = [(lambda x=x: cb.value_proj(x, w, b, mask, num_heads=wl.num_heads)) for x in xs]
         lib = [(lambda x=x: F.linear(x, w, b).masked_fill(mask[..., None], 0.0).unflatten(-1, (wl.num_heads, -1))) for x in xs]
         gemm_only = [(lambda x=x: F.linear(x, w, b)) for x in xs]
@@ -109,11 +111,14 @@ def main():
                 os.environ["MSDA_B200_VPROJ_CLUSTER"] = str(c)
                 g_cluster[f"graphed_value_proj_cluster{c}_us"] = time_graphed(ours)
             os.environ.pop("MSDA_B200_VPROJ_CLUSTER")
+            os.environ["MSDA_B200_VPROJ_NSPLIT"] = "1"
+            g_cluster["graphed_value_proj_nsplit1_us"] = time_graphed(ours)
+            os.environ.pop("MSDA_B200_VPROJ_NSPLIT")
             os.environ["MSDA_B200_VPROJ_SINGLE_TILE"] = "1"
             g_single = time_graphed(ours)
             os.environ.pop("MSDA_B200_VPROJ_SINGLE_TILE")
         # the consumer side: output_proj + residual (same kernel, residual epilogue) vs Linear followed by an add
-        res = [torch.randn(batch, wl.S, N, device=dev).to(dt) for _ in range(n_sets)]
+        res = [torch.randn(batch, keys, N, device=dev).to(dt) for _ in range(n_sets)]
         ours_o = [(lambda x=x, r=r: cb.output_proj(x, w, b, r)) for x, r in zip(xs, res)]
         lib_o = [(lambda x=x, r=r: F.linear(x, w, b) + r) for x, r in zip(xs, res)]
         with torch.inference_mode():

@@ -116,6 +116,33 @@ def test_value_proj_narrow_outputs_many_tiles_per_cta(fin, fout, cuda_device):
     assert float((got.float() - lib.float()).abs().max()) <= float(4.0 * ULP[torch.float16] * lib.float().abs().max() + 1e-6)
 
 
+@pytest.mark.parametrize("bs,keys,fout", [(1, 100, 256), (1, 900, 256), (2, 2000, 256), (1, 4700, 256), (1, 1000, 128)])
+def test_column_split_for_few_row_tiles_is_bit_identical(bs, keys, fout, cuda_device, monkeypatch):
+    """With few row tiles the launcher splits every tile's output columns over 2 or 4 CTAs (each loads only its slice of
+    the weights).  Same MMAs per output element: bit-identical to the unsplit launch, for both entry points."""
+    for dtype in (torch.float16, torch.bfloat16):
+        x, w, b, m = _case(cuda_device, dtype, bs, keys, 256, fout, seed=keys)
+        res = torch.randn(bs, keys, fout, device=cuda_device).to(dtype)
+        monkeypatch.setenv("MSDA_B200_VPROJ_NSPLIT", "1")
+        want_v, want_o = cb.value_proj(x, w, b, m), cb.output_proj(x, w, b, res)
+        assert "/nsplit1/" in cb.last_variant()
+        seen = set()
+        for forced in ("2", "4", None):
+            if forced is None:
+                monkeypatch.delenv("MSDA_B200_VPROJ_NSPLIT")
+            else:
+                monkeypatch.setenv("MSDA_B200_VPROJ_NSPLIT", forced)
+            got_v = cb.value_proj(x, w, b, m)
+            seen.add(cb.last_variant().split("/nsplit")[1][0])
+            got_o = cb.output_proj(x, w, b, res)
+            torch.cuda.synchronize()
+            assert torch.equal(got_v, want_v) and torch.equal(got_o, want_o)
+        tiles = -(-bs * keys // 128)
+        if tiles * 2 <= 148 and fout % 128 == 0:
+            assert seen & {"2", "4"}, seen  # the automatic choice splits when it can
+        _check(want_v, _reference(x, w, b, m), dtype, m)
+
+
 def test_value_proj_output_is_the_ops_value_layout(cuda_device):
     x, w, b, m = _case(cuda_device, torch.float16, 2, 200, 256, 256)
     v = cb.value_proj(x, w, b, m, num_heads=8)
