@@ -760,13 +760,16 @@ static int launch_projection(const void *x, const void *weight, const void *bias
       else if (tiles * 2 <= (unsigned)sms && N % 128 == 0) n_split = 2;
       if (const char *ne = getenv("MSDA_B200_VPROJ_NSPLIT")) {
         const int forced = atoi(ne);
-        if ((forced == 1 || forced == 2 || forced == 4) && N % (64 * forced) == 0 && tiles * (unsigned)forced <= (unsigned)sms) n_split = forced;
+        if ((forced == 1 || forced == 2 || forced == 4) && N % (64 * forced) == 0) n_split = forced;
       }
     }
     if (n_split > 1) {
       p.N = N / n_split;
       p.n_split = n_split;
+      // CTA j owns column block j % n_split for good and walks the row tiles j / n_split, + grid / n_split, ...
       grid = tiles * (unsigned)n_split;
+      const unsigned fit = (unsigned)sms / (unsigned)n_split * (unsigned)n_split;
+      if (grid > fit) grid = fit;
       if (!make_map(&map_w, weight, bf16, (uint64_t)K, (uint64_t)N, (uint32_t)p.N)) return MSDA_ERR_UNSUPPORTED;
     }
     if (cluster > 1) {

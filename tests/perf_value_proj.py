@@ -111,8 +111,9 @@ def main():
                 os.environ["MSDA_B200_VPROJ_CLUSTER"] = str(c)
                 g_cluster[f"graphed_value_proj_cluster{c}_us"] = time_graphed(ours)
             os.environ.pop("MSDA_B200_VPROJ_CLUSTER")
-            os.environ["MSDA_B200_VPROJ_NSPLIT"] = "1"
-            g_cluster["graphed_value_proj_nsplit1_us"] = time_graphed(ours)
+            for ns in (1, 2, 4):
+                os.environ["MSDA_B200_VPROJ_NSPLIT"] = str(ns)
+                g_cluster[f"graphed_value_proj_nsplit{ns}_us"] = time_graphed(ours)
             os.environ.pop("MSDA_B200_VPROJ_NSPLIT")
             os.environ["MSDA_B200_VPROJ_SINGLE_TILE"] = "1"
             g_single = time_graphed(ours)
