@@ -1,4 +1,4 @@
-"""Seeded shape fuzzing of the forward path against the C oracle (GPU tier).
+"""Seeded shape fuzzing of the forward, fused-producer and backward paths against the C oracle (GPU tier).
 
 The fixed cases elsewhere follow the reference's tests and the BASELINE configurations; this file walks 48 random
 (B, M, D, L, P, level sizes, Q, dtype, flags) combinations -- head counts that do not divide a warp, channel counts
@@ -85,3 +85,29 @@ def test_random_shapes_fused_producers_against_oracle(seed, cuda_device):
     torch.cuda.synchronize()
     err = rel_l2(got.cpu().numpy(), want)
     assert err <= 2e-5, f"(B,S,M,D,L,P,Q,ref_dim)={(B, S, M, D, L, P, Q, ref_dim)} {cb.last_variant()}: rel_l2={err:.3e}"
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_random_shapes_backward_against_oracle(seed, cuda_device):
+    """The same walk for the backward entry point (fp32 and fp64): the three gradients against the C oracle's.  Uniform
+    random locations do not land on integer pixel coordinates, where the bilinear gradient has a kink."""
+    arrs, dims = _random_case(200 + seed)
+    B, S, M, D, L, P, Q = dims
+    dtype, np_dt, gate = (torch.float64, np.float64, 1e-12) if seed % 2 else (torch.float32, np.float32, 2e-5)
+    rng = np.random.default_rng(seed)
+    go = rng.standard_normal((B, Q, M * D)).astype(np_dt)
+    cast = {k: (v if v.dtype == np.int64 else v.astype(np_dt)) for k, v in arrs.items()}
+    d = {k: torch.from_numpy(v).to(cuda_device) for k, v in cast.items()}
+    gv = torch.zeros_like(d["value"])
+    gl = torch.full_like(d["sampling_loc"], float("nan"))
+    gw = torch.full_like(d["attn_weight"], float("nan"))
+    cb.backward_into(d["value"], d["spatial_shapes"], d["level_start_index"], d["sampling_loc"], d["attn_weight"],
+                     torch.from_numpy(go).to(cuda_device), gv, gl, gw)
+    torch.cuda.synchronize()
+    o_gv, o_gl, o_gw = oracle.backward_c(cast["value"], cast["spatial_shapes"], cast["level_start_index"], cast["sampling_loc"],
+                                         cast["attn_weight"], go)
+    for name, got, want in (("grad_value", gv, o_gv), ("grad_sampling_loc", gl, o_gl), ("grad_attn_weight", gw, o_gw)):
+        g = got.cpu().numpy()
+        assert not np.isnan(g).any(), f"{name} not fully written, dims={dims} {cb.last_variant()}"
+        err = rel_l2(g, want)
+        assert err <= gate, f"{name}: dims (B,S,M,D,L,P,Q)={dims} {dtype} {cb.last_variant()}: rel_l2={err:.3e}"
