@@ -684,8 +684,9 @@ __device__ __forceinline__ void pdl_wait_prior_grid() { asm volatile("griddepcon
 
 // One bulk L2 prefetch per CTA (cp.async.bulk.prefetch.L2): the CTAs of image blockIdx.y cover its value tensor, so
 // the whole pyramid streams into L2 at HBM rate while the first units compute.  Without it every first touch of a
-// value row is a DRAM-latency miss, and a warp waits for the slowest of the 128 row loads of a sample (measured
-// cold vs L2-warm: 49 vs 44 us at the headline shape).  A no-op when the producer kernel left `value` in L2.
+// value row is a DRAM-latency miss, and a warp waits for the slowest of the 128 row loads of a sample.  Worth
+// 0.3 us at the headline shape (which runs within 0.5 us of its all-L2-warm time either way,
+// tests/perf_cold_parts.py) and 5-7 % on the small shapes.  A no-op when the producer kernel left `value` in L2.
 __device__ __forceinline__ void prefetch_value_l2(const MsdaParams &p, int elem_bytes) {
   if (!p.l2_prefetch || threadIdx.x != 64) return;  // a thread with no set-up work
   const size_t bytes = (size_t)p.S * p.M * p.D * elem_bytes;
