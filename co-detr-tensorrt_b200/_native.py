@@ -64,6 +64,7 @@ FLAG_STAGE_TMA = 1 << 5
 FLAG_NO_PACKED = 1 << 6
 FLAG_HEAD_MAJOR = 1 << 7
 FLAG_PDL = 1 << 8
+FLAG_NO_SMEM_LEVELS = 1 << 9
 
 
 class NativeLibraryError(RuntimeError):

@@ -1,0 +1,235 @@
+// msda_fwd_hp.cuh -- "head-pair" sampling kernel: the coarse pyramid levels live in shared memory.
+// Textually included by msda_sm100.cu (same translation unit: it uses that file's helpers).
+//
+// Why: tools/gather_probe.cu measured what one B200 SM can gather (profiles/r02_gather_probe.jsonl):
+//   * 64-byte rows through LDG (any vector width, L1 hit or miss):  1.0 row / clk / SM   -> 31.5 us for the
+//     9.2 M live corner rows of the 1152x768 encoder call; round 1's kernel ran at 64 % of that;
+//   * the same rows through LDS.128 from shared memory:              1.94 rows / clk / SM when the two lane
+//     groups of a quarter-warp sit on opposite halves of the 32 banks, 1.33 when they do not;
+//   * TMA (tile::gather4 / cp.async.bulk per row):                   0.30 / 0.13 rows / clk / SM.
+// So the only way under the LDG bound is to serve part of the gather from shared memory.  A whole level for
+// all 8 heads does not fit (level 2 of the 1152x768 pyramid is 442 KB), but a PAIR of heads does: levels 2-4
+// are 1,134 pixels x 2 heads x 64 B = 145 KB, and they receive 52 % of the live corner rows.  Hence:
+//   * one CTA per SM, 1,024 threads, owns one head pair (blockIdx.x % (M/2)) of one image (blockIdx.y) and copies
+//     the coarsest levels that fit into its dynamic shared memory as [pixel][2 heads][64 B] -- the natural
+//     layout, in which head parity IS the bank half;
+//   * a warp works on 4 consecutive queries x the 2 heads: lanes 0-3 / 4-7 of every quarter-warp hold heads
+//     2k / 2k+1 of the same query, so every LDS.128 quarter is conflict-free whatever pixels are sampled;
+//   * fine levels are gathered from global memory exactly like the round-1 kernel (LDG.E.128 per lane).
+// Everything else follows msda_fwd_vec: one lane of a group works out the geometry of one point of the level
+// and broadcasts index + packed weights by shuffle; "does not contribute" is a weight of exactly zero, which
+// predicates the load and its FMAs off; fp16 multiplies with FHFMA; the first sample of the next unit is
+// loaded while the current unit is computed.  Which levels are cached is decided on the device from the
+// device-resident shapes (the launcher never reads them), against the shared-memory size it was launched with.
+//
+// Reference semantics: ms_deform_attn.cu:31-77 (bilinear helper), :218-260 (sample loop).
+
+#ifndef MSDA_HP_THREADS
+#define MSDA_HP_THREADS 768
+#endif
+constexpr int kHpThreads = MSDA_HP_THREADS;
+#ifndef MSDA_HP_MAXNREG
+#define MSDA_HP_MAXNREG 64
+#endif
+constexpr int kHpMaxLevels = 8;
+
+struct HpLevel {
+  int H, W;
+  int start;  // first key of the level in the value tensor
+  int srow;   // first 128-byte entry of the level in shared memory (cached levels only)
+};
+
+__device__ __forceinline__ uint4 lds128(unsigned addr) {
+  uint4 r;
+  asm("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+  return r;
+}
+
+// The four samples of one level for this lane group.  `rb` is the lane's row base: a 32-bit shared address
+// (SMEM: cached level, 128-byte pixel pitch) or a 64-bit global address (PIXB-byte pixel pitch).
+template <typename T, int MATH, bool SMEM, int PIXB>
+__device__ __forceinline__ void hp_level_samples(float (&acc)[8], int i00, unsigned pk0, unsigned pk1, const float (&cw)[4], int W,
+                                                 const char *vm, unsigned sm_lane) {
+  constexpr unsigned group_mask = 0xffffffffu;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    uint4 rows[4];
+    float bw[4];
+    unsigned bp0 = 0, bp1 = 0;
+    const int bi = __shfl_sync(group_mask, i00, k, 4);
+    if constexpr (MATH == kFhfma) {
+      bp0 = __shfl_sync(group_mask, pk0, k, 4);
+      bp1 = __shfl_sync(group_mask, pk1, k, 4);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bw[j] = __shfl_sync(group_mask, cw[j], k, 4);
+    }
+    bool on[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if constexpr (MATH == kFhfma) on[j] = ((((j & 2) ? bp1 : bp0) >> ((j & 1) * 16)) & 0x7fffu) != 0u;
+      else on[j] = bw[j] != 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int idx = bi + (j & 1) + ((j & 2) ? W : 0);
+      if (on[j]) {
+        if constexpr (SMEM) rows[j] = lds128(sm_lane + (unsigned)idx * 128u);
+        else rows[j] = ldg128(vm + (size_t)(unsigned)idx * (size_t)PIXB);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if constexpr (MATH == kFhfma) {
+        const unsigned w16 = (((j & 2) ? bp1 : bp0) >> ((j & 1) * 16)) & 0xffffu;
+        if (on[j]) RowFma<T, kFhfma>::run(acc, rows[j], 0.f, w16);
+      } else {
+        if (on[j]) RowFma<T, kExact>::run(acc, rows[j], bw[j], 0u);
+      }
+    }
+  }
+}
+
+// T: __half / __nv_bfloat16, D = 32, P = 4, MT heads (compile time: the neighbour-pixel offset is an immediate).
+template <typename T, int MATH, int MT>
+__global__ void __launch_bounds__(kHpThreads, 1) msda_fwd_hp(const MsdaParams p) {
+  constexpr int D = 32, E = 2, VEC = 8;
+  extern __shared__ __align__(128) unsigned char hp_rows[];  // cached levels: [pixel][2 heads][64 B]
+  __shared__ HpLevel lv[kHpMaxLevels];
+  __shared__ int s_first_cached;
+
+  pdl_launch_dependents();
+  pdl_wait_prior_grid();
+
+  constexpr int M = MT;
+  const int NG = M >> 1;                      // head pairs
+  const int hg = (int)blockIdx.x % NG;        // this CTA's head pair
+  const int rank = (int)blockIdx.x / NG;      // this CTA among those of the head pair
+  const int cpg = (int)gridDim.x / NG;        // CTAs per head pair (the host launches a multiple of NG)
+  const int b = blockIdx.y;
+  const unsigned pix_bytes = (unsigned)(M * D * E);
+  const char *__restrict__ value = static_cast<const char *>(p.value);
+  const T *__restrict__ loc = static_cast<const T *>(p.loc);
+  const T *__restrict__ wgt = static_cast<const T *>(p.weight);
+  T *__restrict__ out = static_cast<T *>(p.out);
+
+  // ---- level table; which levels fit into the shared memory this launch was given ----
+  if (threadIdx.x < p.L) {
+    const int l = threadIdx.x;
+    lv[l].H = (int)__ldg(p.shapes + 2 * l);
+    lv[l].W = (int)__ldg(p.shapes + 2 * l + 1);
+    lv[l].start = (int)__ldg(p.starts + l);
+    lv[l].srow = 0;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long used = 0;
+    int l0 = p.L;
+    for (int l = p.L - 1; l >= 0; --l) {
+      const long long n = (long long)lv[l].H * lv[l].W;
+      const bool ok = lv[l].H > 0 && lv[l].W > 0 && lv[l].start >= 0 && (long long)lv[l].start + n <= (long long)p.S &&
+                      used + n * 128 <= (long long)p.hp_smem_bytes;
+      if (!ok) break;
+      used += n * 128;
+      l0 = l;
+    }
+    int off = 0;
+    for (int l = l0; l < p.L; ++l) {
+      lv[l].srow = off;
+      off += lv[l].H * lv[l].W;
+    }
+    s_first_cached = l0;
+  }
+  __syncthreads();
+  const int l0 = s_first_cached;
+
+  // ---- copy the cached levels: 128 contiguous bytes (the head pair) per pixel ----
+  for (int l = l0; l < p.L; ++l) {
+    const int n8 = lv[l].H * lv[l].W * 8;
+    const char *src = value + ((size_t)b * p.S + (size_t)lv[l].start) * pix_bytes + (size_t)hg * 128;
+    unsigned char *dst = hp_rows + (size_t)lv[l].srow * 128;
+#pragma unroll 4
+    for (int i = threadIdx.x; i < n8; i += kHpThreads) {
+      const int pix = i >> 3, c = i & 7;
+      *reinterpret_cast<uint4 *>(dst + (size_t)pix * 128 + c * 16) = ldg128(src + (size_t)pix * pix_bytes + c * 16);
+    }
+  }
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int grp = lane >> 2, sub = lane & 3;
+  const int qi = grp >> 1, hh = grp & 1;  // query of the warp's four, head of the pair
+  const int m = hg * 2 + hh;
+  const int LP = p.L * 4;
+  const int units = (p.Q + 3) >> 2;
+  const int stride = cpg * (kHpThreads / 32);
+  const char *vm = value + ((size_t)b * p.S * M + m) * (size_t)(D * E) + (size_t)sub * 16;
+  asm volatile("" : "+l"(vm));  // one opaque 64-bit base: every corner address is a single IMAD.WIDE
+  const unsigned sm_lane = smem_u32(hp_rows) + (unsigned)(hh * 64 + sub * 16);
+
+  // Per-image bases are uniform; inside an image this lane's next sample is addressed by ONE running 32-bit byte
+  // offset into the locations (its weight sits at half that offset: both arrays are [Q, M, L*4] with 4- and 2-byte
+  // entries).  The host takes this kernel only when an image's locations are below 4 GB.
+  const char *loc_b = reinterpret_cast<const char *>(loc) + (size_t)b * p.Q * M * LP * (2 * E);
+  const char *wgt_b = reinterpret_cast<const char *>(wgt) + (size_t)b * p.Q * M * LP * E;
+  // offset of point `sub` of level 0 of the pair that unit uu gives this lane group; padding slots (tail of the
+  // last quad, units past the end) read pair 0 of the image and contribute / store nothing
+  auto unit_offset = [&](int uu) -> unsigned {
+    const int q = 4 * uu + qi;
+    return ((uu < units && q < p.Q) ? (unsigned)(q * M + m) * (unsigned)(LP * 2 * E) : 0u) + (unsigned)sub * 4u;
+  };
+  auto load_sample = [&](unsigned o) -> RawSample {
+    RawSample r;
+    r.a = ld_stream_u32(loc_b + (size_t)o);
+    r.b = 0u;
+    r.w = (unsigned)ld_stream_u16(wgt_b + (size_t)(o >> 1));
+    return r;
+  };
+
+  // Unit loop with a trip count that is uniform by construction (that of warp 0 of this CTA): ptxas cannot prove
+  // that a bound depending on threadIdx.x >> 5 is warp-uniform, and with a possibly divergent loop around the
+  // shuffles it emitted divergence fall-backs plus a register copy per predicated load / FMA (46.9 M instead of
+  // 21 M instructions per call).  A warp whose last unit lies past the end runs it with every lane dead.
+  const int first = rank * (kHpThreads / 32);
+  const int iters = first < units ? (units - first + stride - 1) / stride : 0;
+  int u = first + warp;
+  unsigned off = unit_offset(u);  // offset of the sample held in `raw`
+  RawSample raw = load_sample(off);
+
+#pragma unroll 1
+  for (int it = 0; it < iters; ++it, u += stride) {
+    const bool live = u < units && 4 * u + qi < p.Q;
+    float acc[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+
+    // one level: geometry of this lane's point, then the four samples of the lane group
+    auto level = [&](int l, auto smem_tag) {
+      constexpr bool kSmem = decltype(smem_tag)::value;
+      const int H = lv[l].H, W = lv[l].W;
+      float x, y, aw;
+      decode_raw<T>(raw, x, y, aw);
+      aw = live ? aw : 0.f;
+      // prefetch: this lane's sample of the next level, or of the first level of the next unit
+      off = (l + 1 < p.L) ? off + 16u : unit_offset(u + stride);
+      raw = load_sample(off);
+      int i00;
+      float cw[4];
+      make_geo(x, y, aw, H, W, i00, cw);
+      unsigned pk0 = 0, pk1 = 0;
+      if constexpr (MATH == kFhfma) {
+        pk0 = pack_weights<T>(cw[0], cw[1]);
+        pk1 = pack_weights<T>(cw[2], cw[3]);
+      }
+      i00 += kSmem ? lv[l].srow : lv[l].start;
+      hp_level_samples<T, MATH, kSmem, MT * D * E>(acc, i00, pk0, pk1, cw, W, vm, sm_lane);
+    };
+    // fine levels from global memory, then the cached coarse levels from shared memory
+#pragma unroll 1
+    for (int l = 0; l < l0; ++l) level(l, std::false_type{});
+#pragma unroll 1
+    for (int l = l0; l < p.L; ++l) level(l, std::true_type{});
+
+    if (live) store_row<T, VEC>(out + ((size_t)b * p.Q * M + (size_t)(4 * u + qi) * M + m) * D + sub * VEC, acc);
+  }
+}

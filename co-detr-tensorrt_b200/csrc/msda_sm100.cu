@@ -153,6 +153,7 @@ struct MsdaParams {
   int pdl_early_tables; // 1: (MSDA_FLAG_PDL) read the level tables before waiting for the preceding kernel
   int l2_prefetch;      // 1: every CTA starts by asking L2 to fetch its share of the image's value tensor
   unsigned *sched;      // dynamic unit scheduling: {next warp-unit, finished warps} counters of this launch, or nullptr
+  int hp_smem_bytes;    // head-pair kernel: dynamic shared memory available for cached pyramid levels
 };
 
 struct LevelGeom {
@@ -1458,6 +1459,8 @@ __global__ void __launch_bounds__(kSmallThreads, 8) msda_fwd_small(const MsdaPar
   if (live && split == 0) store_row<T, VEC>(out + pair * D + sub * VEC, acc);
 }
 
+#include "msda_fwd_hp.cuh"
+
 // ---------------------------------------------------------------------------
 // Packed path (16-bit types, D = 32, P = 4): pixel-pair packed pyramid + 256-bit loads.
 //
@@ -2288,6 +2291,42 @@ int forward_impl(MsdaParams p, int dtype, unsigned flags, void *workspace, size_
         snprintf(g_last_variant, sizeof(g_last_variant), "small<%s,D%d,P4,split4>/%s", dtype_name(dtype), p.D,
                  plan.math == kFhfma ? "fhfma" : "exact");
       return rc3;
+    }
+  }
+
+  // ---- head-pair kernel: coarse levels in shared memory (msda_fwd_hp.cuh) ----
+  // 16-bit types, D = 32, P = 4, an even number of heads, and enough query quads to give every warp of every
+  // CTA work; MSDA_FLAG_NO_SMEM_LEVELS / MSDA_B200_HP=0 fall back to the all-global kernel below.
+  {
+    const int NG = p.M / 2;
+    const bool hp_shape = E == 2 && p.D == 32 && p.P == 4 && p.M == 8 && p.L >= 1 && p.L <= kHpMaxLevels &&
+                          NG <= sms && !fused && plan.split == 1 && plan.stage_bytes == 0 && !plan.dyn &&
+                          aligned_to(p.loc, 4) && !(flags & MSDA_FLAG_NO_SMEM_LEVELS);
+    const int cpg = NG > 0 ? sms / NG : 0;
+    const int64_t quads = ((int64_t)p.Q + 3) / 4;
+    const int64_t hp_min_quads = (int64_t)env_int("MSDA_B200_HP_MIN_QUADS_PER_WARP", 2) * cpg * (kHpThreads / 32);
+    if (hp_shape && env_int("MSDA_B200_HP", 1) && quads >= hp_min_quads && !(workspace != nullptr && env_int("MSDA_B200_PACKED", 1))) {
+      p.hp_smem_bytes = env_int("MSDA_B200_HP_SMEM", 148 * 1024);
+      if (p.hp_smem_bytes < 0) p.hp_smem_bytes = 0;
+      if (p.hp_smem_bytes > 200 * 1024) p.hp_smem_bytes = 200 * 1024;
+      const dim3 hgrid((unsigned)(cpg * NG), (unsigned)p.B, 1);
+      auto launch_hp = [&](auto kernel) -> int {
+        cudaError_t ae = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p.hp_smem_bytes);
+        if (ae != cudaSuccess) return (int)ae;
+        const cudaError_t le = launch_kernel(kernel, hgrid, dim3(kHpThreads), (size_t)p.hp_smem_bytes, stream, plan.pdl, p);
+        g_launch_count.fetch_add(1, std::memory_order_relaxed);
+        return le != cudaSuccess ? (int)le : (int)cudaGetLastError();
+      };
+      int rch;
+      if (dtype == MSDA_F16) {
+        rch = plan.math == kFhfma ? launch_hp(msda_fwd_hp<__half, kFhfma, 8>) : launch_hp(msda_fwd_hp<__half, kExact, 8>);
+      } else {
+        rch = plan.math == kFhfma ? launch_hp(msda_fwd_hp<__nv_bfloat16, kFhfma, 8>) : launch_hp(msda_fwd_hp<__nv_bfloat16, kExact, 8>);
+      }
+      if (rch == 0)
+        snprintf(g_last_variant, sizeof(g_last_variant), "hp<%s,D32,P4,M%d>/smem%dK/%s", dtype_name(dtype), p.M, p.hp_smem_bytes / 1024,
+                 plan.math == kFhfma ? "fhfma" : "exact");
+      return rch;
     }
   }
 

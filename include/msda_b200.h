@@ -75,6 +75,8 @@ enum msda_flags {
                                        measured slightly slower than direct loads) */
   MSDA_FLAG_NO_PACKED = 1 << 6,     /* ignore the workspace: never use the packed-pyramid path */
   MSDA_FLAG_HEAD_MAJOR = 1 << 7,    /* a warp holds one head of neighbouring queries (default: query-major) */
+  MSDA_FLAG_NO_SMEM_LEVELS = 1 << 9, /* never use the head-pair kernel that keeps the coarse pyramid levels in
+                                       shared memory (msda_fwd_hp); every level is gathered from global memory */
   MSDA_FLAG_PDL = 1 << 8            /* The launches always carry the programmatic-stream-serialization attribute
                                        (CTAs may be scheduled while the preceding kernel of the stream drains; all
                                        reads wait for that kernel -- semantics are plain stream order).  This flag

@@ -24,6 +24,10 @@ sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active
 l1tex__throughput.avg.pct_of_peak_sustained_active
 l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed
 l1tex__data_pipe_lsu_wavefronts.sum
+l1tex__data_pipe_lsu_wavefronts_mem_shared.sum
+l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum
+smsp__inst_executed_op_shared_ld.sum
+smsp__inst_executed_op_global_ld.sum
 l1tex__lsu_writeback_active.avg.pct_of_peak_sustained_elapsed
 l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum
 l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum
