@@ -9,7 +9,7 @@ Importing the package loads ``csrc/libmsda_b200.so`` and registers
 the library has not been built: there is no CPU or PyTorch fallback.
 """
 from . import _native
-from ._native import (FLAG_FORCE_GENERIC, FLAG_LINEAR_ORDER, FLAG_MATH_EXACT, FLAG_HEAD_MAJOR, FLAG_MATH_FHFMA, FLAG_PDL, FLAG_NO_PACKED, FLAG_NO_STAGING, FLAG_STAGE_TMA,
+from ._native import (FLAG_FORCE_GENERIC, FLAG_LINEAR_ORDER, FLAG_MATH_EXACT, FLAG_HEAD_MAJOR, FLAG_MATH_FHFMA, FLAG_PDL, FLAG_NO_PACKED, FLAG_NO_SMEM_LEVELS, FLAG_NO_STAGING, FLAG_STAGE_TMA,
                       NativeLibraryError, build_native, last_variant, launch_count)
 from . import workloads
 from . import sharding
@@ -22,6 +22,6 @@ from .ops import (HostForward, HostPipeline, PreparedForward, backward_into, for
 __all__ = [
     "MultiScaleDeformableAttention", "multi_scale_deformable_attention", "forward_into", "backward_into", "forward_fused", "plugin_enqueue", "HostForward", "HostPipeline", "PreparedForward",
     "set_default_flags", "read_bandwidth_probe", "build_native", "launch_count", "last_variant", "workloads", "sharding",
-    "FLAG_FORCE_GENERIC", "FLAG_LINEAR_ORDER", "FLAG_MATH_EXACT", "FLAG_MATH_FHFMA", "FLAG_NO_STAGING", "FLAG_STAGE_TMA", "FLAG_NO_PACKED", "FLAG_HEAD_MAJOR", "FLAG_PDL", "workspace_bytes", "set_use_workspace",
+    "FLAG_FORCE_GENERIC", "FLAG_LINEAR_ORDER", "FLAG_MATH_EXACT", "FLAG_MATH_FHFMA", "FLAG_NO_STAGING", "FLAG_STAGE_TMA", "FLAG_NO_PACKED", "FLAG_NO_SMEM_LEVELS", "FLAG_HEAD_MAJOR", "FLAG_PDL", "workspace_bytes", "set_use_workspace",
     "NativeLibraryError", "value_proj", "value_proj_supported", "output_proj",
 ]

@@ -22,7 +22,7 @@ INCLUDE_DIR = os.path.join(_REPO_ROOT, "include")
 # MSDA_B200_LIB lets tuning experiments load an alternative build of the same sources
 LIB_PATH = os.environ.get("MSDA_B200_LIB") or os.path.join(CSRC_DIR, "libmsda_b200.so")
 SOURCES = [os.path.join(CSRC_DIR, "msda_sm100.cu"), os.path.join(CSRC_DIR, "value_proj_sm100.cu")]
-HEADERS = [os.path.join(INCLUDE_DIR, "msda_b200.h"), os.path.join(CSRC_DIR, "msda_internal.hpp")]
+HEADERS = [os.path.join(INCLUDE_DIR, "msda_b200.h"), os.path.join(CSRC_DIR, "msda_internal.hpp"), os.path.join(CSRC_DIR, "msda_fwd_hp.cuh")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

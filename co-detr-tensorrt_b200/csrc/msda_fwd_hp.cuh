@@ -25,7 +25,7 @@
 // Reference semantics: ms_deform_attn.cu:31-77 (bilinear helper), :218-260 (sample loop).
 
 #ifndef MSDA_HP_THREADS
-#define MSDA_HP_THREADS 768
+#define MSDA_HP_THREADS 800
 #endif
 constexpr int kHpThreads = MSDA_HP_THREADS;
 #ifndef MSDA_HP_MAXNREG
@@ -35,8 +35,8 @@ constexpr int kHpMaxLevels = 8;
 
 struct HpLevel {
   int H, W;
+  int base;   // first key of the level in the value tensor, or (cached level) its first 128-byte entry in shared memory
   int start;  // first key of the level in the value tensor
-  int srow;   // first 128-byte entry of the level in shared memory (cached levels only)
 };
 
 __device__ __forceinline__ uint4 lds128(unsigned addr) {
@@ -70,13 +70,21 @@ __device__ __forceinline__ void hp_level_samples(float (&acc)[8], int i00, unsig
       if constexpr (MATH == kFhfma) on[j] = ((((j & 2) ? bp1 : bp0) >> ((j & 1) * 16)) & 0x7fffu) != 0u;
       else on[j] = bw[j] != 0.f;
     }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int idx = bi + (j & 1) + ((j & 2) ? W : 0);
-      if (on[j]) {
-        if constexpr (SMEM) rows[j] = lds128(sm_lane + (unsigned)idx * 128u);
-        else rows[j] = ldg128(vm + (size_t)(unsigned)idx * (size_t)PIXB);
-      }
+    // two row addresses per sample (top-left, bottom-left); the right-hand corners are immediate offsets
+    if constexpr (SMEM) {
+      const unsigned s0 = sm_lane + (unsigned)bi * 128u, s1 = s0 + (unsigned)W * 128u;
+      if (on[0]) rows[0] = lds128(s0);
+      if (on[1]) rows[1] = lds128(s0 + 128u);
+      if (on[2]) rows[2] = lds128(s1);
+      if (on[3]) rows[3] = lds128(s1 + 128u);
+    } else {
+      // signed: the top-left index is -1 (or -1 - W) when only right-hand / lower corners are inside the level
+      const char *g0 = vm + (ptrdiff_t)bi * (ptrdiff_t)PIXB;
+      const char *g1 = vm + (ptrdiff_t)(bi + W) * (ptrdiff_t)PIXB;
+      if (on[0]) rows[0] = ldg128(g0);
+      if (on[1]) rows[1] = ldg128(g0 + PIXB);
+      if (on[2]) rows[2] = ldg128(g1);
+      if (on[3]) rows[3] = ldg128(g1 + PIXB);
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -119,7 +127,7 @@ __global__ void __launch_bounds__(kHpThreads, 1) msda_fwd_hp(const MsdaParams p)
     lv[l].H = (int)__ldg(p.shapes + 2 * l);
     lv[l].W = (int)__ldg(p.shapes + 2 * l + 1);
     lv[l].start = (int)__ldg(p.starts + l);
-    lv[l].srow = 0;
+    lv[l].base = lv[l].start;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -135,7 +143,7 @@ __global__ void __launch_bounds__(kHpThreads, 1) msda_fwd_hp(const MsdaParams p)
     }
     int off = 0;
     for (int l = l0; l < p.L; ++l) {
-      lv[l].srow = off;
+      lv[l].base = off;
       off += lv[l].H * lv[l].W;
     }
     s_first_cached = l0;
@@ -147,9 +155,9 @@ __global__ void __launch_bounds__(kHpThreads, 1) msda_fwd_hp(const MsdaParams p)
   for (int l = l0; l < p.L; ++l) {
     const int n8 = lv[l].H * lv[l].W * 8;
     const char *src = value + ((size_t)b * p.S + (size_t)lv[l].start) * pix_bytes + (size_t)hg * 128;
-    unsigned char *dst = hp_rows + (size_t)lv[l].srow * 128;
+    unsigned char *dst = hp_rows + (size_t)lv[l].base * 128;
 #pragma unroll 4
-    for (int i = threadIdx.x; i < n8; i += kHpThreads) {
+    for (int i = threadIdx.x; i < n8; i += (int)blockDim.x) {
       const int pix = i >> 3, c = i & 7;
       *reinterpret_cast<uint4 *>(dst + (size_t)pix * 128 + c * 16) = ldg128(src + (size_t)pix * pix_bytes + c * 16);
     }
@@ -162,7 +170,8 @@ __global__ void __launch_bounds__(kHpThreads, 1) msda_fwd_hp(const MsdaParams p)
   const int m = hg * 2 + hh;
   const int LP = p.L * 4;
   const int units = (p.Q + 3) >> 2;
-  const int stride = cpg * (kHpThreads / 32);
+  const int nw = (int)blockDim.x >> 5;  // warps per CTA: chosen by the host so that the units divide evenly
+  const int stride = cpg * nw;
   const char *vm = value + ((size_t)b * p.S * M + m) * (size_t)(D * E) + (size_t)sub * 16;
   asm volatile("" : "+l"(vm));  // one opaque 64-bit base: every corner address is a single IMAD.WIDE
   const unsigned sm_lane = smem_u32(hp_rows) + (unsigned)(hh * 64 + sub * 16);
@@ -190,46 +199,67 @@ __global__ void __launch_bounds__(kHpThreads, 1) msda_fwd_hp(const MsdaParams p)
   // that a bound depending on threadIdx.x >> 5 is warp-uniform, and with a possibly divergent loop around the
   // shuffles it emitted divergence fall-backs plus a register copy per predicated load / FMA (46.9 M instead of
   // 21 M instructions per call).  A warp whose last unit lies past the end runs it with every lane dead.
-  const int first = rank * (kHpThreads / 32);
+  const int first = rank * nw;
   const int iters = first < units ? (units - first + stride - 1) / stride : 0;
   int u = first + warp;
-  unsigned off = unit_offset(u);  // offset of the sample held in `raw`
-  RawSample raw = load_sample(off);
+  auto is_live = [&](int uu) { return uu < units && 4 * uu + qi < p.Q; };
+
+  // Software pipeline over (unit, level) steps, two deep: while the four samples of step t are gathered and
+  // accumulated, the geometry of step t+1 (this lane's point of the next level, or of level 0 of the next
+  // unit) is worked out from inputs loaded during step t-1, and the inputs of step t+2 are requested.  The
+  // geometry chain (un-normalise, floor, weights, pack: ~15 dependent instructions) and the location / weight
+  // loads therefore never sit between a warp and its next row loads.  Needs L >= 2 (host-checked).
+  struct Geo {
+    int i00, W;
+    unsigned pk0, pk1;
+    float cw[4];
+  };
+  auto geometry = [&](const RawSample &rw, int l, bool lv_live) -> Geo {
+    Geo g;
+    const int H = lv[l].H;
+    g.W = lv[l].W;
+    float x, y, aw;
+    decode_raw<T>(rw, x, y, aw);
+    aw = lv_live ? aw : 0.f;
+    make_geo(x, y, aw, H, g.W, g.i00, g.cw);
+    g.i00 += lv[l].base;
+    g.pk0 = g.pk1 = 0u;
+    if constexpr (MATH == kFhfma) {
+      g.pk0 = pack_weights<T>(g.cw[0], g.cw[1]);
+      g.pk1 = pack_weights<T>(g.cw[2], g.cw[3]);
+    }
+    return g;
+  };
+  unsigned off = unit_offset(u);            // offset of the inputs held in `raw`
+  bool live = is_live(u);
+  Geo geo = geometry(load_sample(off), 0, live);  // step 0
+  off += 16u;
+  RawSample raw = load_sample(off);         // inputs of step 1 (level 1 of the first unit)
 
 #pragma unroll 1
   for (int it = 0; it < iters; ++it, u += stride) {
-    const bool live = u < units && 4 * u + qi < p.Q;
+    const bool live_n = is_live(u + stride);
     float acc[VEC];
 #pragma unroll
     for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
 
-    // one level: geometry of this lane's point, then the four samples of the lane group
-    auto level = [&](int l, auto smem_tag) {
+    auto step = [&](int l, auto smem_tag) {
       constexpr bool kSmem = decltype(smem_tag)::value;
-      const int H = lv[l].H, W = lv[l].W;
-      float x, y, aw;
-      decode_raw<T>(raw, x, y, aw);
-      aw = live ? aw : 0.f;
-      // prefetch: this lane's sample of the next level, or of the first level of the next unit
-      off = (l + 1 < p.L) ? off + 16u : unit_offset(u + stride);
+      // geometry of step t+1 from the inputs in `raw`; request the inputs of step t+2
+      const bool wrap = l + 1 >= p.L;
+      const Geo next = geometry(raw, wrap ? 0 : l + 1, wrap ? live_n : live);
+      off = (l + 2 == p.L) ? unit_offset(u + stride) : off + 16u;
       raw = load_sample(off);
-      int i00;
-      float cw[4];
-      make_geo(x, y, aw, H, W, i00, cw);
-      unsigned pk0 = 0, pk1 = 0;
-      if constexpr (MATH == kFhfma) {
-        pk0 = pack_weights<T>(cw[0], cw[1]);
-        pk1 = pack_weights<T>(cw[2], cw[3]);
-      }
-      i00 += kSmem ? lv[l].srow : lv[l].start;
-      hp_level_samples<T, MATH, kSmem, MT * D * E>(acc, i00, pk0, pk1, cw, W, vm, sm_lane);
+      hp_level_samples<T, MATH, kSmem, MT * D * E>(acc, geo.i00, geo.pk0, geo.pk1, geo.cw, geo.W, vm, sm_lane);
+      geo = next;
     };
     // fine levels from global memory, then the cached coarse levels from shared memory
 #pragma unroll 1
-    for (int l = 0; l < l0; ++l) level(l, std::false_type{});
+    for (int l = 0; l < l0; ++l) step(l, std::false_type{});
 #pragma unroll 1
-    for (int l = l0; l < p.L; ++l) level(l, std::true_type{});
+    for (int l = l0; l < p.L; ++l) step(l, std::true_type{});
 
     if (live) store_row<T, VEC>(out + ((size_t)b * p.Q * M + (size_t)(4 * u + qi) * M + m) * D + sub * VEC, acc);
+    live = live_n;
   }
 }

@@ -2299,21 +2299,47 @@ int forward_impl(MsdaParams p, int dtype, unsigned flags, void *workspace, size_
   // CTA work; MSDA_FLAG_NO_SMEM_LEVELS / MSDA_B200_HP=0 fall back to the all-global kernel below.
   {
     const int NG = p.M / 2;
-    const bool hp_shape = E == 2 && p.D == 32 && p.P == 4 && p.M == 8 && p.L >= 1 && p.L <= kHpMaxLevels &&
+    const bool hp_shape = E == 2 && p.D == 32 && p.P == 4 && p.M == 8 && p.L >= 2 && p.L <= kHpMaxLevels &&
                           NG <= sms && !fused && plan.split == 1 && plan.stage_bytes == 0 && !plan.dyn &&
                           aligned_to(p.loc, 4) && !(flags & MSDA_FLAG_NO_SMEM_LEVELS);
     const int cpg = NG > 0 ? sms / NG : 0;
     const int64_t quads = ((int64_t)p.Q + 3) / 4;
     const int64_t hp_min_quads = (int64_t)env_int("MSDA_B200_HP_MIN_QUADS_PER_WARP", 2) * cpg * (kHpThreads / 32);
+    // Warps per CTA: every warp of the cpg CTAs of a head pair walks the query quads with the same stride, so the
+    // call takes ceil(quads / (cpg * nw)) rounds; pick the nw (of the upper half of what the register budget
+    // allows) that wastes the least of the last round -- 4,604 quads over 37 CTAs: 24 warps -> 6 rounds, 86 %
+    // busy; 25 warps -> 5 rounds, 99.5 %.
+    int hp_warps = kHpThreads / 32;
+    {
+      double best = -1.0;
+      for (int nw = kHpThreads / 32; nw >= kHpThreads / 64 && cpg > 0; --nw) {
+        const int64_t per_round = (int64_t)cpg * nw;
+        const int64_t rounds = (quads + per_round - 1) / per_round;
+        const double eff = rounds > 0 ? (double)quads / (double)(rounds * per_round) : 0.0;
+        // fewer warps hide less latency: a configuration with half the warps must be 14 % better balanced to win
+        const double score = eff * (0.75 + 0.25 * (double)nw / (double)(kHpThreads / 32));
+        if (score > best + 1e-4) {
+          best = score;
+          hp_warps = nw;
+        }
+      }
+      hp_warps = env_int("MSDA_B200_HP_WARPS", hp_warps);
+      if (hp_warps < 1) hp_warps = 1;
+      if (hp_warps > kHpThreads / 32) hp_warps = kHpThreads / 32;
+    }
     if (hp_shape && env_int("MSDA_B200_HP", 1) && quads >= hp_min_quads && !(workspace != nullptr && env_int("MSDA_B200_PACKED", 1))) {
-      p.hp_smem_bytes = env_int("MSDA_B200_HP_SMEM", 148 * 1024);
+      // Cached levels: the copy into shared memory costs every CTA ~1.5 us up front and takes L1 capacity away from
+      // the fine levels; measured neutral at 5 rounds per warp (headline, 45.2 vs 44.9 us), -3 % at 20 rounds
+      // (strides 4-64: 164.7 vs 170.2 us), +33 % on a 1,900-query decoder call.  So: only for long calls.
+      const int64_t hp_rounds = (quads + (int64_t)cpg * hp_warps - 1) / ((int64_t)cpg * hp_warps);
+      p.hp_smem_bytes = env_int("MSDA_B200_HP_SMEM", hp_rounds >= 12 ? 148 * 1024 : 0);
       if (p.hp_smem_bytes < 0) p.hp_smem_bytes = 0;
       if (p.hp_smem_bytes > 200 * 1024) p.hp_smem_bytes = 200 * 1024;
       const dim3 hgrid((unsigned)(cpg * NG), (unsigned)p.B, 1);
       auto launch_hp = [&](auto kernel) -> int {
         cudaError_t ae = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p.hp_smem_bytes);
         if (ae != cudaSuccess) return (int)ae;
-        const cudaError_t le = launch_kernel(kernel, hgrid, dim3(kHpThreads), (size_t)p.hp_smem_bytes, stream, plan.pdl, p);
+        const cudaError_t le = launch_kernel(kernel, hgrid, dim3((unsigned)hp_warps * 32u), (size_t)p.hp_smem_bytes, stream, plan.pdl, p);
         g_launch_count.fetch_add(1, std::memory_order_relaxed);
         return le != cudaSuccess ? (int)le : (int)cudaGetLastError();
       };
@@ -2324,8 +2350,8 @@ int forward_impl(MsdaParams p, int dtype, unsigned flags, void *workspace, size_
         rch = plan.math == kFhfma ? launch_hp(msda_fwd_hp<__nv_bfloat16, kFhfma, 8>) : launch_hp(msda_fwd_hp<__nv_bfloat16, kExact, 8>);
       }
       if (rch == 0)
-        snprintf(g_last_variant, sizeof(g_last_variant), "hp<%s,D32,P4,M%d>/smem%dK/%s", dtype_name(dtype), p.M, p.hp_smem_bytes / 1024,
-                 plan.math == kFhfma ? "fhfma" : "exact");
+        snprintf(g_last_variant, sizeof(g_last_variant), "hp<%s,D32,P4,M%d>/smem%dK/%dwarps/%s", dtype_name(dtype), p.M,
+                 p.hp_smem_bytes / 1024, hp_warps, plan.math == kFhfma ? "fhfma" : "exact");
       return rch;
     }
   }

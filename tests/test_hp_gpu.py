@@ -1,0 +1,139 @@
+"""GPU tier: the head-pair kernel (msda_fwd_hp: coarse pyramid levels cached in shared memory, fine levels from
+global memory) against the all-global vector kernel and the C oracle.
+
+Both kernels run the same arithmetic in the same order for a (query, head) pair, so for every shape, dtype, math
+mode and shared-memory budget the outputs must be bit-identical; parity with the reference then follows from the
+vector kernel's own tests, and is re-checked here against the C oracle (oracle/msda_oracle.c, which restates
+ms_deform_attn.cu:31-77 / :218-260) on shapes built to hit every branch of the new kernel.
+"""
+import numpy as np
+import pytest
+import torch
+
+import codetr_b200 as cb
+import oracle
+from codetr_b200 import workloads as W
+from parity import BF16_MAX_REL, HALF_MAX_REL, max_rel
+
+pytestmark = pytest.mark.gpu
+
+KEYS = ("value", "spatial_shapes", "level_start_index", "sampling_loc", "attn_weight")
+DT = {"f16": torch.float16, "bf16": torch.bfloat16}
+
+
+def _inputs(shapes, Q, B, seed, out_of_range=0.0, kind="encoder"):
+    wl = W.Workload(name="hp_test", shapes=tuple(shapes), num_queries=Q, batch=B, kind=kind, seed=seed)
+    return W.make_inputs(wl, out_of_range_frac=out_of_range)
+
+
+def _dev(inp, dt, device):
+    d = {}
+    for k in KEYS:
+        t = torch.from_numpy(np.ascontiguousarray(getattr(inp, k)))
+        d[k] = t.to(device) if t.dtype == torch.int64 else t.to(device=device, dtype=dt)
+    return d
+
+
+def _run(d, flags=0):
+    out = cb.multi_scale_deformable_attention(*(d[k] for k in KEYS), 64, flags=flags)
+    torch.cuda.synchronize()
+    return out, cb.last_variant()
+
+
+# (pyramid, queries (0 = encoder: one per key), batch): query counts that are not multiples of 4, a batch, a pyramid
+# whose coarse levels fit the shared-memory budget and one where only the last level does
+SHAPES = [
+    (W.pyramid_shapes(384, 256), 0, 1),
+    (W.pyramid_shapes(384, 256), 0, 3),
+    (W.pyramid_shapes(256, 384), 2501, 2),
+    (((40, 60), (20, 30), (10, 15)), 3333, 1),          # 3 levels
+    (((64, 64), (32, 32)), 4099, 1),                      # 2 levels (the pipeline's minimum)
+]
+
+
+@pytest.mark.parametrize("dt", ["f16", "bf16"])
+@pytest.mark.parametrize("smem_kb", [0, 8, 36, 148, 200])
+@pytest.mark.parametrize("shape_id", range(len(SHAPES)))
+def test_head_pair_kernel_is_bit_identical_to_vector_kernel(shape_id, smem_kb, dt, cuda_device, monkeypatch):
+    shapes, Q, B = SHAPES[shape_id]
+    kind = "encoder" if Q == 0 else "decoder"
+    inp = _inputs(shapes, Q, B, seed=11 + shape_id, out_of_range=0.05, kind=kind)
+    d = _dev(inp, DT[dt], cuda_device)
+    monkeypatch.setenv("MSDA_B200_SPLIT", "1")                      # the fixtures are small: keep them off the small-problem kernel
+    monkeypatch.setenv("MSDA_B200_HP_MIN_QUADS_PER_WARP", "0")
+    monkeypatch.setenv("MSDA_B200_HP_SMEM", str(smem_kb * 1024))
+    for fl in (0, cb.FLAG_MATH_EXACT, cb.FLAG_MATH_FHFMA):
+        want, v0 = _run(d, fl | cb.FLAG_NO_SMEM_LEVELS)
+        assert v0.startswith("vec<"), v0
+        before = cb.launch_count()
+        got, v1 = _run(d, fl)
+        assert cb.launch_count() == before + 1
+        assert v1.startswith("hp<") and f"smem{smem_kb}K" in v1, v1
+        assert torch.equal(got, want), f"{v1} differs from {v0}: max abs {float((got.float() - want.float()).abs().max())}"
+    # and against the C oracle (fp32 reference on the rounded inputs)
+    ref = oracle.forward_c(d["value"].float().cpu().numpy(), inp.spatial_shapes, inp.level_start_index,
+                           d["sampling_loc"].float().cpu().numpy(), d["attn_weight"].float().cpu().numpy())
+    got, _ = _run(d, 0)
+    assert max_rel(got.float().cpu().numpy(), ref) <= (HALF_MAX_REL if dt == "f16" else BF16_MAX_REL)
+
+
+@pytest.mark.parametrize("warps", [1, 7, 16, 25])
+def test_head_pair_kernel_any_warp_count(warps, cuda_device, monkeypatch):
+    """The host picks the warps per CTA that balances the rounds; every count must give the same bits (including
+    counts that leave whole warps without a unit)."""
+    inp = _inputs(W.pyramid_shapes(256, 256), 0, 2, seed=5, out_of_range=0.1)
+    d = _dev(inp, torch.float16, cuda_device)
+    monkeypatch.setenv("MSDA_B200_SPLIT", "1")
+    monkeypatch.setenv("MSDA_B200_HP_MIN_QUADS_PER_WARP", "0")
+    monkeypatch.setenv("MSDA_B200_HP_SMEM", str(148 * 1024))
+    want, _ = _run(d, cb.FLAG_NO_SMEM_LEVELS)
+    monkeypatch.setenv("MSDA_B200_HP_WARPS", str(warps))
+    got, v = _run(d, 0)
+    assert v.startswith("hp<") and f"/{warps}warps/" in v, v
+    assert torch.equal(got, want)
+
+
+def test_head_pair_kernel_output_fully_written_and_graph_safe(cuda_device, monkeypatch):
+    """Caller-owned NaN-filled output, external stream, CUDA-graph capture and replay: the kernel neither
+    allocates nor synchronises, and writes every element."""
+    monkeypatch.setenv("MSDA_B200_SPLIT", "1")
+    monkeypatch.setenv("MSDA_B200_HP_MIN_QUADS_PER_WARP", "0")
+    monkeypatch.setenv("MSDA_B200_HP_SMEM", str(148 * 1024))
+    inp = _inputs(W.pyramid_shapes(320, 224), 0, 2, seed=9, out_of_range=0.05)
+    d = _dev(inp, torch.float16, cuda_device)
+    want, _ = _run(d, cb.FLAG_NO_SMEM_LEVELS)
+    out = torch.full_like(want, float("nan"))
+    side = torch.cuda.Stream(device=cuda_device)
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        cb.forward_into(*(d[k] for k in KEYS), out)
+        assert cb.last_variant().startswith("hp<")
+        g = torch.cuda.CUDAGraph()
+        out2 = torch.full_like(want, float("nan"))
+        with torch.cuda.graph(g, stream=side):
+            cb.forward_into(*(d[k] for k in KEYS), out2)
+    torch.cuda.synchronize()
+    assert torch.equal(out, want)
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out2, want)
+
+
+def test_head_pair_kernel_non_finite_locations(cuda_device, monkeypatch):
+    """NaN / infinite sampling locations fail the reference's range test (ms_deform_attn.cu:249): the sample
+    contributes nothing and nothing is read for it."""
+    monkeypatch.setenv("MSDA_B200_SPLIT", "1")
+    monkeypatch.setenv("MSDA_B200_HP_MIN_QUADS_PER_WARP", "0")
+    monkeypatch.setenv("MSDA_B200_HP_SMEM", str(148 * 1024))
+    inp = _inputs(W.pyramid_shapes(256, 256), 0, 1, seed=21)
+    loc = inp.sampling_loc.copy()
+    rng = np.random.default_rng(3)
+    bad = rng.random(loc.shape[:-1]) < 0.05
+    loc[bad] = rng.choice(np.array([np.nan, np.inf, -np.inf, 1e30, -1e30], dtype=loc.dtype), size=(int(bad.sum()), 1))
+    d = _dev(inp, torch.float16, cuda_device)
+    d["sampling_loc"] = torch.from_numpy(loc).to(device=cuda_device, dtype=torch.float16)
+    want, _ = _run(d, cb.FLAG_NO_SMEM_LEVELS)
+    got, v = _run(d, 0)
+    assert v.startswith("hp<")
+    assert not torch.isnan(got).any()
+    assert torch.equal(got, want)
