@@ -37,6 +37,25 @@ int to_msda_dtype(at::ScalarType t) {
     TORCH_CHECK(false, "ms_deform_attn_forward: unsupported dtype ", t);
   }
 }
+
+// Extent / device agreement between the five inputs: what the reference's fake kernel asserts at trace time
+// (codetr/ops.py:59-84).  The C ABI trusts its caller's sizes, so a mismatch here would become an out-of-bounds
+// device read instead of an error.
+void check_extents(const at::Tensor &value, const at::Tensor &spatial_shapes, const at::Tensor &level_start_index,
+                   const at::Tensor &sampling_loc, const at::Tensor &attn_weight) {
+  TORCH_CHECK(level_start_index.dim() == 1 && attn_weight.dim() == 5, "unexpected tensor ranks");
+  TORCH_CHECK(spatial_shapes.size(1) == 2, "spatial_shapes must be [num_levels, 2]");
+  TORCH_CHECK(level_start_index.size(0) == spatial_shapes.size(0), "level_start_index must have one entry per level");
+  TORCH_CHECK(sampling_loc.size(0) == value.size(0) && sampling_loc.size(2) == value.size(2) &&
+                  sampling_loc.size(3) == spatial_shapes.size(0) && sampling_loc.size(5) == 2,
+              "sampling_loc must be [batch, num_query, num_heads, num_levels, num_points, 2]");
+  for (int axis = 0; axis < 5; ++axis)
+    TORCH_CHECK(attn_weight.size(axis) == sampling_loc.size(axis), "attn_weight must match sampling_loc on axis ", axis);
+  const auto dev = value.device();
+  TORCH_CHECK(spatial_shapes.device() == dev && level_start_index.device() == dev && sampling_loc.device() == dev &&
+                  attn_weight.device() == dev,
+              "all tensors must be on the same CUDA device");
+}
 } // namespace
 
 void ms_deform_attn_forward_reference(const at::Tensor &value, const at::Tensor &spatial_shapes,
@@ -58,6 +77,8 @@ void ms_deform_attn_forward_reference(const at::Tensor &value, const at::Tensor 
   TORCH_CHECK(sampling_loc.scalar_type() == value.scalar_type() && attn_weight.scalar_type() == value.scalar_type() &&
                   output.scalar_type() == value.scalar_type(),
               "value, sampling_loc, attn_weight and output must share one dtype");
+  check_extents(value, spatial_shapes, level_start_index, sampling_loc, attn_weight);
+  TORCH_CHECK(output.device() == value.device(), "output must be on the same CUDA device");
 
   const int64_t batch = value.size(0), num_keys = value.size(1), num_heads = value.size(2), channels = value.size(3);
   const int64_t num_levels = spatial_shapes.size(0);
@@ -111,6 +132,10 @@ void ms_deform_attn_backward(const at::Tensor &value, const at::Tensor &spatial_
   TORCH_CHECK(grad_value.sizes() == value.sizes() && grad_sampling_loc.sizes() == sampling_loc.sizes() &&
                   grad_attn_weight.sizes() == attn_weight.sizes(),
               "gradient shapes must match their tensors");
+  check_extents(value, spatial_shapes, level_start_index, sampling_loc, attn_weight);
+  TORCH_CHECK(grad_output.dim() == 3 && grad_output.size(0) == value.size(0) && grad_output.size(1) == sampling_loc.size(1) &&
+                  grad_output.size(2) == value.size(2) * value.size(3),
+              "grad_output must be [batch, num_query, num_heads * channels]");
   const c10::cuda::CUDAGuard device_guard(value.device());
   cudaStream_t stream = at::cuda::getCurrentCUDAStream();
   const int rc = msda_b200_backward(value.data_ptr(), spatial_shapes.data_ptr<int64_t>(), level_start_index.data_ptr<int64_t>(),

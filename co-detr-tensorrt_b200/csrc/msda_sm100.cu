@@ -2130,7 +2130,12 @@ int forward_impl(MsdaParams p, int dtype, unsigned flags, void *workspace, size_
   // ---- choose the kernel ----
   bool vec_ok = !(flags & MSDA_FLAG_FORCE_GENERIC) && dtype != MSDA_F64 &&
                 (p.D == 16 || p.D == 32 || p.D == 64) && p.L <= kMaxLevelsSmem &&
-                aligned_to(p.value, 16) && aligned_to(p.out, 16) && ((size_t)p.M * p.D * E) % 16 == 0;
+                aligned_to(p.value, 16) && aligned_to(p.out, 16) && ((size_t)p.M * p.D * E) % 16 == 0 &&
+                // the fast paths read an (x, y) pair with one load: a contiguous view at an odd element offset takes
+                // the element-wise kernel instead of faulting
+                aligned_to(fused ? p.offsets : p.loc, 2 * E) &&
+                // nothing to sample (L*P == 0, pointers may be NULL): the element-wise kernel writes the zeros
+                p.L > 0 && p.P > 0;
   const int G = vec_ok ? (int)(p.D * E / 16) : 1;
   // the fused-producer mode lives on the broadcast path only (P = 4, rows of at least four lanes)
   if (fused && !(p.P == 4 && G >= 4)) vec_ok = false;
@@ -2271,13 +2276,14 @@ int forward_impl(MsdaParams p, int dtype, unsigned flags, void *workspace, size_
       using TT = decltype(tag_t);
       constexpr int DD = decltype(tag_d)::value;
       if constexpr (DD * (int)sizeof(TT) / 16 * 4 <= 32) {
+        cudaError_t se = cudaSuccess;
         if (sizeof(TT) == 2 && plan.math == kFhfma) {
-          if constexpr (sizeof(TT) == 2) launch_kernel(msda_fwd_small<TT, DD, kFhfma>, dim3(sgrid), dim3(kSmallThreads), 0, stream, plan.pdl, p);
+          if constexpr (sizeof(TT) == 2) se = launch_kernel(msda_fwd_small<TT, DD, kFhfma>, dim3(sgrid), dim3(kSmallThreads), 0, stream, plan.pdl, p);
         } else {
-          launch_kernel(msda_fwd_small<TT, DD, kExact>, dim3(sgrid), dim3(kSmallThreads), 0, stream, plan.pdl, p);
+          se = launch_kernel(msda_fwd_small<TT, DD, kExact>, dim3(sgrid), dim3(kSmallThreads), 0, stream, plan.pdl, p);
         }
         g_launch_count.fetch_add(1, std::memory_order_relaxed);
-        rc3 = (int)cudaGetLastError();
+        rc3 = se != cudaSuccess ? (int)se : (int)cudaGetLastError();
       }
     };
     if (dtype == MSDA_F16 && p.D == 32) launch_small(__half{}, std::integral_constant<int, 32>{});
@@ -2438,6 +2444,7 @@ const char *msda_b200_error_string(int code) {
     case MSDA_ERR_MISALIGNED: return "msda_b200: pointer not aligned to its element size";
     case MSDA_ERR_UNSUPPORTED: return "msda_b200: shape outside the supported index range";
     case MSDA_ERR_BAD_FLAGS: return "msda_b200: contradictory flags";
+    case MSDA_ERR_WORKSPACE_TOO_SMALL: return "msda_b200: workspace smaller than the matching *_workspace_bytes()";
     default: break;
   }
   if (code > 0) return cudaGetErrorString((cudaError_t)code);
@@ -2591,7 +2598,8 @@ int msda_b200_forward_host(const void *value_host, const int64_t *spatial_shapes
   const size_t E = elem_size(dtype);
   if (E == 0) return MSDA_ERR_BAD_DTYPE;
   if (B < 0 || S < 0 || M < 0 || D < 0 || L < 0 || Q < 0 || P < 0) return MSDA_ERR_BAD_SHAPE;
-  if (!workspace_dev || workspace_bytes < msda_b200_host_workspace_bytes(B, S, M, D, L, Q, P, dtype)) return MSDA_ERR_NULL_POINTER;
+  if (!workspace_dev) return MSDA_ERR_NULL_POINTER;
+  if (workspace_bytes < msda_b200_host_workspace_bytes(B, S, M, D, L, Q, P, dtype)) return MSDA_ERR_WORKSPACE_TOO_SMALL;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   char *ws = static_cast<char *>(workspace_dev);
   const size_t n_val = (size_t)B * S * M * D * E, n_shp = (size_t)L * 16, n_st = (size_t)L * 8;

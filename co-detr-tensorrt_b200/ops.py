@@ -60,13 +60,19 @@ _use_workspace = False
 
 
 def set_use_workspace(enabled: bool) -> bool:
+    """Give the registered torch op a scratch buffer per call (packed-pyramid path).  Applies to the Python
+    registration and to :func:`multi_scale_deformable_attention`; the native registration
+    (``codetr_b200_torch.so``, ``op_registration == "native"``) always runs the library defaults -- set
+    ``MSDA_B200_PYTHON_OP=1`` before importing the package to route the op through Python instead."""
     global _use_workspace
     old, _use_workspace = _use_workspace, bool(enabled)
     return old
 
 
 def set_default_flags(flags: int) -> int:
-    """Launch flags (``_native.FLAG_*``) applied by the registered torch op."""
+    """Launch flags (``_native.FLAG_*``) applied by the registered torch op.  Like :func:`set_use_workspace` this
+    reaches the Python registration only; the native registration passes ``MSDA_FLAG_DEFAULT`` (the library's
+    ``MSDA_B200_*`` environment knobs still apply to both)."""
     global _default_flags
     old, _default_flags = _default_flags, int(flags)
     return old
@@ -441,6 +447,7 @@ class HostPipeline:
         self._events = [None] * self.depth
         self._ws = [None] * self.depth
         self._out = [None] * self.depth
+        self._inputs = [None] * self.depth  # host tensors of the slot's call in flight (kept alive for the async copies)
         self._next = 0
 
     def submit(self, value: Tensor, spatial_shapes: Tensor, level_start_index: Tensor, sampling_loc: Tensor,
@@ -451,6 +458,7 @@ class HostPipeline:
         self._next = (self._next + 1) % self.depth
         if self._events[slot] is not None:
             self._events[slot].synchronize()  # the slot's previous call (and its output copy) has finished
+            self._inputs[slot] = None
         bs, keys, heads, chans = value.shape
         queries, levels, points = sampling_loc.shape[1], sampling_loc.shape[3], sampling_loc.shape[4]
         dt = _DTYPES[value.dtype]
@@ -472,10 +480,17 @@ class HostPipeline:
             ev = torch.cuda.Event()
             ev.record(stream)
             self._events[slot] = ev
+            # the copies are asynchronous: hold the caller's host tensors until the slot's event has completed, so a
+            # temporary (e.g. ``x.pin_memory()``) cannot be recycled by the host allocator while the DMA reads it.
+            # The CONTENTS are still the caller's: do not write to an input before ``result(ticket)`` returns.
+            self._inputs[slot] = (value, spatial_shapes, level_start_index, sampling_loc, attn_weight)
         return slot
 
     def result(self, ticket: int) -> Tensor:
+        """The call's output: the slot's pinned host buffer, valid until ``depth`` further ``submit`` calls reuse
+        the slot -- copy it if it has to live longer."""
         self._events[ticket].synchronize()
+        self._inputs[ticket] = None
         return self._out[ticket]
 
     def drain(self) -> None:

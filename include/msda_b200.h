@@ -59,7 +59,8 @@ enum msda_error {
   MSDA_ERR_BAD_STEP = -4,       /* B % min(B, im2col_step) != 0 (ms_deform_attn.cu:924-926) */
   MSDA_ERR_MISALIGNED = -5,     /* a pointer is not aligned to its element size       */
   MSDA_ERR_UNSUPPORTED = -6,    /* shape outside what the kernels index (e.g. > 2^31 keys) */
-  MSDA_ERR_BAD_FLAGS = -7
+  MSDA_ERR_BAD_FLAGS = -7,
+  MSDA_ERR_WORKSPACE_TOO_SMALL = -8 /* a caller-provided workspace is smaller than the matching *_workspace_bytes() */
 };
 
 /* Launch flags (bit field).  0 = library defaults. */

@@ -236,6 +236,9 @@ def test_bench_reference_arm_runs_on_cpu():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "images/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+    # the reference arm runs none of this repo's native code: the product library is not even mapped
+    assert line["product_so_loaded"] == []
+    assert line["config"]["workload"] == "r50_enc_608" and line["config"]["Q"] == 7706 and line["config"]["B"] == 1
 
 
 def test_missing_native_library_fails_loudly():
@@ -270,3 +273,26 @@ def test_numa_binding_is_a_safe_no_op_without_a_gpu():
     if prev is not None:
         os.sched_setaffinity(0, prev)
     assert os.sched_getaffinity(0) == before
+
+
+def test_registered_overload_is_what_the_dynamo_converter_keys_on():
+    """The reference's Torch-TensorRT converter is registered on `torch.ops.codetr.multi_scale_deformable_attention.default`
+    and reads five tensor inputs plus the `im2col_step` int from the node's args (/root/reference/codetr/ops.py:189-291,
+    plugin field built at :253-258): the overload name, arity, argument order / names / types and the single Tensor return
+    of the op this package registers must be exactly that."""
+    import torch
+
+    import codetr_b200  # noqa: F401  (registers the op)
+
+    packet = torch.ops.codetr.multi_scale_deformable_attention
+    assert packet.overloads() == ["default"]
+    schema = packet.default._schema
+    assert schema.name == "codetr::multi_scale_deformable_attention" and schema.overload_name == ""
+    names = [a.name for a in schema.arguments]
+    types = [str(a.type) for a in schema.arguments]
+    assert names == ["value", "spatial_shapes", "level_start_index", "sampling_loc", "attn_weight", "im2col_step"]
+    assert types == ["Tensor"] * 5 + ["int"]
+    assert [str(r.type) for r in schema.returns] == ["Tensor"]
+    assert not any(a.alias_info is not None and a.alias_info.is_write for a in schema.arguments)   # functional: safe to trace
+    bwd = torch.ops.codetr.multi_scale_deformable_attention_backward.default._schema
+    assert [str(a.type) for a in bwd.arguments] == ["Tensor"] * 9 + ["int"]

@@ -35,6 +35,8 @@ l1tex__t_sector_hit_rate.pct
 l1tex__m_xbar2l1tex_read_bytes.sum
 l1tex__m_xbar2l1tex_read_bytes.sum.pct_of_peak_sustained_elapsed
 lts__t_sectors.sum
+lts__t_sectors_op_read.sum
+lts__t_sectors_srcunit_tex_op_read.sum
 lts__t_sector_hit_rate.pct
 lts__throughput.avg.pct_of_peak_sustained_elapsed
 dram__bytes_read.sum
