@@ -2307,6 +2307,9 @@ int forward_impl(MsdaParams p, int dtype, unsigned flags, void *workspace, size_
     const int NG = p.M / 2;
     const bool hp_shape = E == 2 && p.D == 32 && p.P == 4 && p.M == 8 && p.L >= 2 && p.L <= kHpMaxLevels &&
                           NG <= sms && !fused && plan.split == 1 && plan.stage_bytes == 0 && !plan.dyn &&
+                          // exact-arithmetic calls (bf16 default, MSDA_FLAG_MATH_EXACT) stay on the vector kernel, which is
+                          // 3 % faster for them at the headline shape (58.9 vs 60.6 us); MSDA_B200_HP_EXACT=1 overrides
+                          (plan.math == kFhfma || env_int("MSDA_B200_HP_EXACT", 0)) &&
                           aligned_to(p.loc, 4) && !(flags & MSDA_FLAG_NO_SMEM_LEVELS);
     const int cpg = NG > 0 ? sms / NG : 0;
     const int64_t quads = ((int64_t)p.Q + 3) / 4;

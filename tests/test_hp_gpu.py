@@ -61,6 +61,7 @@ def test_head_pair_kernel_is_bit_identical_to_vector_kernel(shape_id, smem_kb, d
     d = _dev(inp, DT[dt], cuda_device)
     monkeypatch.setenv("MSDA_B200_SPLIT", "1")                      # the fixtures are small: keep them off the small-problem kernel
     monkeypatch.setenv("MSDA_B200_HP_MIN_QUADS_PER_WARP", "0")
+    monkeypatch.setenv("MSDA_B200_HP_EXACT", "1")                   # also the exact-arithmetic instantiations (default: vector kernel)
     monkeypatch.setenv("MSDA_B200_HP_SMEM", str(smem_kb * 1024))
     for fl in (0, cb.FLAG_MATH_EXACT, cb.FLAG_MATH_FHFMA):
         want, v0 = _run(d, fl | cb.FLAG_NO_SMEM_LEVELS)
@@ -85,6 +86,7 @@ def test_head_pair_kernel_any_warp_count(warps, cuda_device, monkeypatch):
     d = _dev(inp, torch.float16, cuda_device)
     monkeypatch.setenv("MSDA_B200_SPLIT", "1")
     monkeypatch.setenv("MSDA_B200_HP_MIN_QUADS_PER_WARP", "0")
+    monkeypatch.setenv("MSDA_B200_HP_EXACT", "1")                   # also the exact-arithmetic instantiations (default: vector kernel)
     monkeypatch.setenv("MSDA_B200_HP_SMEM", str(148 * 1024))
     want, _ = _run(d, cb.FLAG_NO_SMEM_LEVELS)
     monkeypatch.setenv("MSDA_B200_HP_WARPS", str(warps))
@@ -98,6 +100,7 @@ def test_head_pair_kernel_output_fully_written_and_graph_safe(cuda_device, monke
     allocates nor synchronises, and writes every element."""
     monkeypatch.setenv("MSDA_B200_SPLIT", "1")
     monkeypatch.setenv("MSDA_B200_HP_MIN_QUADS_PER_WARP", "0")
+    monkeypatch.setenv("MSDA_B200_HP_EXACT", "1")                   # also the exact-arithmetic instantiations (default: vector kernel)
     monkeypatch.setenv("MSDA_B200_HP_SMEM", str(148 * 1024))
     inp = _inputs(W.pyramid_shapes(320, 224), 0, 2, seed=9, out_of_range=0.05)
     d = _dev(inp, torch.float16, cuda_device)
@@ -124,6 +127,7 @@ def test_head_pair_kernel_non_finite_locations(cuda_device, monkeypatch):
     contributes nothing and nothing is read for it."""
     monkeypatch.setenv("MSDA_B200_SPLIT", "1")
     monkeypatch.setenv("MSDA_B200_HP_MIN_QUADS_PER_WARP", "0")
+    monkeypatch.setenv("MSDA_B200_HP_EXACT", "1")                   # also the exact-arithmetic instantiations (default: vector kernel)
     monkeypatch.setenv("MSDA_B200_HP_SMEM", str(148 * 1024))
     inp = _inputs(W.pyramid_shapes(256, 256), 0, 1, seed=21)
     loc = inp.sampling_loc.copy()
