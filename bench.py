@@ -165,42 +165,47 @@ def live_corner_rows(inp) -> int:
     return total
 
 
-def pcie_probe(dev, h2d_bytes: int, d2h_bytes: int, reps: int):
-    """Host-fabric ceiling of this rank: pinned host -> device and device -> host cudaMemcpyAsync of the e2e step's
-    byte counts, both directions in flight at once on two streams, CUDA-event timed.  Returns GB/s (sum of both
-    directions) -- what `e2e` could reach if kernels and host code were free."""
+def pcie_probe(dev, piece_bytes, d2h_bytes: int, reps: int, barrier):
+    """Host-fabric ceiling of this rank while EVERY rank does the same: the e2e step's host -> device pieces and its
+    device -> host result as plain pinned cudaMemcpyAsync calls, no kernel, no library, `reps` steps in steady state,
+    timed on the host between barriers like the e2e leg itself.  Two patterns, both reported (GB/s, both directions summed):
+      free       uploads on one stream, downloads on another, nothing ties them together
+      dependent  the download of step i waits for the upload of step i (the dependency a real call has), 3 output slots
+    An earlier version timed 100 queued copies with CUDA events right after the e2e leg; ranks that started late then
+    measured a half-idle fabric (27.8 GB/s per rank at N = 8 where the steady state gives 18-21), so the ceiling was too high."""
     import torch
 
-    h_in = torch.empty(max(h2d_bytes, 1), dtype=torch.uint8).pin_memory()
-    h_out = torch.empty(max(d2h_bytes, 1), dtype=torch.uint8).pin_memory()
-    h_in.fill_(1)
-    d_in = torch.empty(max(h2d_bytes, 1), dtype=torch.uint8, device=dev)
+    h_in = [torch.empty(max(n, 1), dtype=torch.uint8).pin_memory().fill_(1) for n in piece_bytes]
+    d_in = [torch.empty(max(n, 1), dtype=torch.uint8, device=dev) for n in piece_bytes]
+    h_out = [torch.empty(max(d2h_bytes, 1), dtype=torch.uint8).pin_memory() for _ in range(3)]
     d_out = torch.zeros(max(d2h_bytes, 1), dtype=torch.uint8, device=dev)
     s_up, s_down = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    total = sum(piece_bytes) + d2h_bytes
 
-    def run(n):
-        # the whole queue of each direction is enqueued at once: the two DMA directions then run flat out side by side
-        with torch.cuda.stream(s_up):
-            for _ in range(n):
-                d_in.copy_(h_in, non_blocking=True)
-        with torch.cuda.stream(s_down):
-            for _ in range(n):
-                h_out.copy_(d_out, non_blocking=True)
+    def run(n, dependent):
+        for i in range(n):
+            with torch.cuda.stream(s_up):
+                for dst, src in zip(d_in, h_in):
+                    dst.copy_(src, non_blocking=True)
+                if dependent:
+                    ev = torch.cuda.Event()
+                    ev.record(s_up)
+            with torch.cuda.stream(s_down):
+                if dependent:
+                    s_down.wait_event(ev)
+                h_out[i % 3].copy_(d_out, non_blocking=True)
 
-    run(3)
-    torch.cuda.synchronize(dev)
-    best = 0.0
-    for _ in range(3):
-        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-        e0.record(s_up)
-        s_down.wait_event(e0)
-        run(reps)
-        e1.record(s_up)
-        e2.record(s_down)
+    out = {}
+    for name, dependent in (("free", False), ("dependent", True)):
+        run(3, dependent)
         torch.cuda.synchronize(dev)
-        ms = max(e0.elapsed_time(e1), e0.elapsed_time(e2))
-        best = max(best, (h2d_bytes + d2h_bytes) * reps / (ms * 1e-3) / 1e9)
-    return best
+        barrier()
+        t0 = time.perf_counter()
+        run(reps, dependent)
+        torch.cuda.synchronize(dev)
+        out[name] = total * reps / (time.perf_counter() - t0) / 1e9
+        barrier()
+    return out
 
 
 def pin_rank_to_cores(local: int, world: int):
@@ -633,24 +638,27 @@ def run_b200(args):
         # host-fabric ceiling, measured the same way on every rank AT THE SAME TIME (inside one barrier window): the
         # step's H2D and D2H byte counts as plain pinned copies, both directions in flight -- no kernel, no library
         pipe = None
-        barrier()
-        probe = pcie_probe(dev, h2d, d2h, max(10, min(e2e_steps, 100)))
-        tp = torch.tensor([probe], dtype=torch.float64, device=dev)
-        per_rank_probe = [probe]
+        pieces = [hs[k].numel() * hs[k].element_size() for k in keys]
+        probe = pcie_probe(dev, pieces, d2h, e2e_steps, barrier)
+        tp = torch.tensor([probe["free"], probe["dependent"]], dtype=torch.float64, device=dev)
+        per_rank_probe = [[probe["free"], probe["dependent"]]]
         if use_dist:
             allp = [torch.zeros_like(tp) for _ in range(world)]
             dist.all_gather(allp, tp)
-            per_rank_probe = [float(x.item()) for x in allp]
+            per_rank_probe = [[float(x[0].item()), float(x[1].item())] for x in allp]
         achieved_gbps = (h2d + d2h) * e2e_steps / t_e2e / 1e9  # of the slowest rank
+        slowest_peak = min(max(p) for p in per_rank_probe)      # the better pattern, on the rank that gets least
         e2e = {"value": world * batch * e2e_steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": 1e3 * t_e2e / e2e_steps,
                "pcie_GBps": achieved_gbps,
-               "pcie_peak_GBps": min(per_rank_probe), "frac_of_pcie_peak": achieved_gbps / min(per_rank_probe),
-               "pcie_peak_note": "pinned H2D + D2H cudaMemcpyAsync of the step's byte counts, both directions in flight, all "
-                                 "ranks at once; min over ranks (the max-over-ranks time is set by the slowest rank)",
+               "pcie_peak_GBps": slowest_peak, "frac_of_pcie_peak": achieved_gbps / slowest_peak,
+               "pcie_peak_note": "the step's byte counts as plain pinned cudaMemcpyAsync calls (no kernel, no library), all ranks at "
+                                 "once, same number of steps, host-timed between barriers like the e2e leg; per rank [free, dependent] "
+                                 "= [uploads and downloads on independent streams, download i waits for upload i]; the ceiling is the "
+                                 "better pattern on the rank that gets least (the max-over-ranks time is set by the slowest rank)",
                "per_rank_ms_per_step": per_rank_ms, "per_rank_pcie_peak_GBps": per_rank_probe,
                "aggregate_GBps": sum((h2d + d2h) / (ms * 1e-3) / 1e9 for ms in per_rank_ms),
-               "aggregate_pcie_peak_GBps": sum(per_rank_probe),
+               "aggregate_pcie_peak_GBps": sum(max(p) for p in per_rank_probe),
                "host_cores_per_rank": len(os.sched_getaffinity(0)),
                "synchronous_ms_per_call": 1e3 * t_sync,
                "api": "codetr_b200.HostPipeline(depth=3) -> msda_b200_forward_host (pinned host buffers, "
