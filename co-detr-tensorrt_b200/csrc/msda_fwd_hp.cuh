@@ -121,7 +121,9 @@ __device__ __forceinline__ void hp_level_samples(float (&acc)[8], int i00, unsig
 }
 
 // T: __half / __nv_bfloat16, D = 32, P = 4, MT heads (compile time: the neighbour-pixel offset is an immediate).
-template <typename T, int MATH, int MT>
+// DYN: warps draw (query quad, head pair) units from the launch's device counter instead of striding over their own
+// head pair's quads (no cached levels in that mode: a CTA is no longer tied to one head pair).
+template <typename T, int MATH, int MT, bool DYN = false>
 __global__ void __launch_bounds__(kHpThreads, 1) msda_fwd_hp(const MsdaParams p) {
   constexpr int D = 32, E = 2, VEC = 8;
   extern __shared__ __align__(128) unsigned char hp_rows[];  // cached levels: [pixel][2 heads][64 B]
@@ -194,8 +196,7 @@ __global__ void __launch_bounds__(kHpThreads, 1) msda_fwd_hp(const MsdaParams p)
   const int units = (p.Q + 3) >> 2;
   const int nw = (int)blockDim.x >> 5;  // warps per CTA: chosen by the host so that the units divide evenly
   const int stride = cpg * nw;
-  const char *vm = value + ((size_t)b * p.S * M + m) * (size_t)(D * E) + (size_t)sub * 16;
-  asm volatile("" : "+l"(vm));  // one opaque 64-bit base: every corner address is a single IMAD.WIDE
+  const char *vm_img = value + (size_t)b * p.S * M * (size_t)(D * E) + (size_t)sub * 16;  // head 0 of this image, this lane's 16 bytes
   const unsigned sm_lane = smem_u32(hp_rows) + (unsigned)(hh * 64 + sub * 16);
 
   // Per-image bases are uniform; inside an image this lane's next sample is addressed by ONE running 32-bit byte
@@ -203,11 +204,16 @@ __global__ void __launch_bounds__(kHpThreads, 1) msda_fwd_hp(const MsdaParams p)
   // entries).  The host takes this kernel only when an image's locations are below 4 GB.
   const char *loc_b = reinterpret_cast<const char *>(loc) + (size_t)b * p.Q * M * LP * (2 * E);
   const char *wgt_b = reinterpret_cast<const char *>(wgt) + (size_t)b * p.Q * M * LP * E;
-  // offset of point `sub` of level 0 of the pair that unit uu gives this lane group; padding slots (tail of the
+  // A unit index names a query quad and a head pair.  Static schedule: the CTA's own pair, index = quad.  Dynamic:
+  // index = quad * NG + pair, so warps that draw consecutive indices read adjacent pieces of one query's inputs.
+  auto unit_quad = [&](int idx) { return DYN ? idx / NG : idx; };
+  auto unit_head = [&](int idx) { return (DYN ? idx % NG : hg) * 2 + hh; };
+  const int total = DYN ? units * NG : units;
+  auto is_live = [&](int idx) { return idx < total && 4 * unit_quad(idx) + qi < p.Q; };
+  // offset of point `sub` of level 0 of the pair that unit idx gives this lane group; padding slots (tail of the
   // last quad, units past the end) read pair 0 of the image and contribute / store nothing
-  auto unit_offset = [&](int uu) -> unsigned {
-    const int q = 4 * uu + qi;
-    return ((uu < units && q < p.Q) ? (unsigned)(q * M + m) * (unsigned)(LP * 2 * E) : 0u) + (unsigned)sub * 4u;
+  auto unit_offset = [&](int idx) -> unsigned {
+    return (is_live(idx) ? (unsigned)((4 * unit_quad(idx) + qi) * M + unit_head(idx)) * (unsigned)(LP * 2 * E) : 0u) + (unsigned)sub * 4u;
   };
   auto load_sample = [&](unsigned o) -> RawSample {
     RawSample r;
@@ -216,15 +222,6 @@ __global__ void __launch_bounds__(kHpThreads, 1) msda_fwd_hp(const MsdaParams p)
     r.w = (unsigned)ld_stream_u16(wgt_b + (size_t)(o >> 1));
     return r;
   };
-
-  // Unit loop with a trip count that is uniform by construction (that of warp 0 of this CTA): ptxas cannot prove
-  // that a bound depending on threadIdx.x >> 5 is warp-uniform, and with a possibly divergent loop around the
-  // shuffles it emitted divergence fall-backs plus a register copy per predicated load / FMA (46.9 M instead of
-  // 21 M instructions per call).  A warp whose last unit lies past the end runs it with every lane dead.
-  const int first = rank * nw;
-  const int iters = first < units ? (units - first + stride - 1) / stride : 0;
-  int u = first + warp;
-  auto is_live = [&](int uu) { return uu < units && 4 * uu + qi < p.Q; };
 
   // Software pipeline over (unit, level) steps, two deep: while the four samples of step t are gathered and
   // accumulated, the geometry of step t+1 (this lane's point of the next level, or of level 0 of the next
@@ -252,15 +249,45 @@ __global__ void __launch_bounds__(kHpThreads, 1) msda_fwd_hp(const MsdaParams p)
     }
     return g;
   };
-  unsigned off = unit_offset(u);            // offset of the inputs held in `raw`
-  bool live = is_live(u);
+  // ---- unit schedule ----
+  // Static: this warp's quads rank*nw + warp, + stride, ... with a trip count that is uniform by construction (that
+  // of warp 0 of the CTA).  ptxas cannot prove that a bound depending on threadIdx.x >> 5 is warp-uniform, and with a
+  // possibly divergent loop around the shuffles it emitted divergence fall-backs plus a register copy per predicated
+  // load / FMA (46.9 M instead of 21 M instructions per call); a warp whose last unit lies past the end runs it dead.
+  // Dynamic: indices drawn two ahead from the launch's counter (lane 0 draws, the warp shares the value); the loop
+  // condition is a warp vote, which ptxas does treat as uniform.
+  unsigned *const sched = DYN ? p.sched + (size_t)blockIdx.y * 2 : nullptr;
+  auto draw = [&]() -> int {
+    unsigned v = 0;
+    if (lane == 0) v = atomicAdd(sched, 1u);
+    return (int)__shfl_sync(0xffffffffu, v, 0);
+  };
+  const int first = rank * nw;
+  const int iters = first < units ? (units - first + stride - 1) / stride : 0;
+  int cur, nxt;
+  if constexpr (DYN) {
+    cur = draw();
+    nxt = draw();
+  } else {
+    cur = first + warp;
+    nxt = cur + stride;
+  }
+  const char *vm = vm_img + (size_t)unit_head(cur) * (size_t)(D * E);
+  asm volatile("" : "+l"(vm));  // one opaque 64-bit base: every corner address is a single IMAD.WIDE
+
+  unsigned off = unit_offset(cur);          // offset of the inputs held in `raw`
+  bool live = is_live(cur);
   Geo geo = geometry(load_sample(off), 0, live);  // step 0
   off += 16u;
   RawSample raw = load_sample(off);         // inputs of step 1 (level 1 of the first unit)
 
+  int it = 0;
 #pragma unroll 1
-  for (int it = 0; it < iters; ++it, u += stride) {
-    const bool live_n = is_live(u + stride);
+  while (DYN ? __any_sync(0xffffffffu, cur < total) : it < iters) {
+    int after = 0;
+    if constexpr (DYN) after = draw();      // the unit after next: the atomic's latency hides behind this unit
+    else after = nxt + stride;
+    const bool live_n = is_live(nxt);
     float acc[VEC];
 #pragma unroll
     for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
@@ -270,7 +297,7 @@ __global__ void __launch_bounds__(kHpThreads, 1) msda_fwd_hp(const MsdaParams p)
       // geometry of step t+1 from the inputs in `raw`; request the inputs of step t+2
       const bool wrap = l + 1 >= p.L;
       const Geo next = geometry(raw, wrap ? 0 : l + 1, wrap ? live_n : live);
-      off = (l + 2 == p.L) ? unit_offset(u + stride) : off + 16u;
+      off = (l + 2 == p.L) ? unit_offset(nxt) : off + 16u;
       raw = load_sample(off);
       hp_level_samples<T, MATH, kSmem, MT * D * E>(acc, geo.i00, geo.pk0, geo.pk1, geo.cw, geo.W, vm, sm_lane);
       geo = next;
@@ -281,7 +308,25 @@ __global__ void __launch_bounds__(kHpThreads, 1) msda_fwd_hp(const MsdaParams p)
 #pragma unroll 1
     for (int l = l0; l < p.L; ++l) step(l, std::true_type{});
 
-    if (live) store_row<T, VEC>(out + ((size_t)b * p.Q * M + (size_t)(4 * u + qi) * M + m) * D + sub * VEC, acc);
+    if (live) store_row<T, VEC>(out + ((size_t)b * p.Q * M + (size_t)(4 * unit_quad(cur) + qi) * M + unit_head(cur)) * D + sub * VEC, acc);
     live = live_n;
+    cur = nxt;
+    nxt = after;
+    if constexpr (DYN) {
+      vm = vm_img + (size_t)unit_head(cur) * (size_t)(D * E);
+      asm volatile("" : "+l"(vm));
+    }
+    ++it;
+  }
+  if constexpr (DYN) {
+    // this warp has drawn its last unit; the last warp of the image's grid row to get here re-arms the counters
+    if (lane == 0) {
+      const unsigned finished = atomicAdd(sched + 1, 1u);
+      if (finished == gridDim.x * (unsigned)nw - 1u) {
+        sched[0] = 0u;
+        sched[1] = 0u;
+        __threadfence();
+      }
+    }
   }
 }

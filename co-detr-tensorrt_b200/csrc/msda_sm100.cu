@@ -2352,15 +2352,31 @@ int forward_impl(MsdaParams p, int dtype, unsigned flags, void *workspace, size_
         g_launch_count.fetch_add(1, std::memory_order_relaxed);
         return le != cudaSuccess ? (int)le : (int)cudaGetLastError();
       };
+      // Dynamic unit scheduling (MSDA_B200_HP_DYN=1, opt-in): warps draw (quad, head pair) units from a device counter
+      // to take out the 4 % spread between the fastest and the slowest SM of the static schedule.  Bit-identical, clean
+      // code (the loop condition is a warp vote, which ptxas treats as uniform) -- and 16 % SLOWER (headline 51.9 vs
+      // 44.5 us, R50 32.0 vs 21.5): 18,416 atomics on one address per launch serialise in one L2 slice at ~3 ns each,
+      // which is longer than the kernel.  Drawing chunks would cut the atomics but leave 1.2 chunks of 4 per warp, a
+      // worse balance than the static one.  Only without cached levels and outside stream capture.
+      bool hp_dyn = false;
+      if (p.hp_smem_bytes == 0 && env_int("MSDA_B200_HP_DYN", 0)) {
+        p.sched = sched_slots(p.B, stream);
+        hp_dyn = p.sched != nullptr;
+        // no rounds to fill evenly any more: as many warps as the register budget allows
+        if (hp_dyn) hp_warps = env_int("MSDA_B200_HP_WARPS", kHpThreads / 32);
+        if (hp_warps < 1 || hp_warps > kHpThreads / 32) hp_warps = kHpThreads / 32;
+      }
       int rch;
       if (dtype == MSDA_F16) {
-        rch = plan.math == kFhfma ? launch_hp(msda_fwd_hp<__half, kFhfma, 8>) : launch_hp(msda_fwd_hp<__half, kExact, 8>);
+        if (hp_dyn) rch = plan.math == kFhfma ? launch_hp(msda_fwd_hp<__half, kFhfma, 8, true>) : launch_hp(msda_fwd_hp<__half, kExact, 8, true>);
+        else rch = plan.math == kFhfma ? launch_hp(msda_fwd_hp<__half, kFhfma, 8>) : launch_hp(msda_fwd_hp<__half, kExact, 8>);
       } else {
-        rch = plan.math == kFhfma ? launch_hp(msda_fwd_hp<__nv_bfloat16, kFhfma, 8>) : launch_hp(msda_fwd_hp<__nv_bfloat16, kExact, 8>);
+        if (hp_dyn) rch = plan.math == kFhfma ? launch_hp(msda_fwd_hp<__nv_bfloat16, kFhfma, 8, true>) : launch_hp(msda_fwd_hp<__nv_bfloat16, kExact, 8, true>);
+        else rch = plan.math == kFhfma ? launch_hp(msda_fwd_hp<__nv_bfloat16, kFhfma, 8>) : launch_hp(msda_fwd_hp<__nv_bfloat16, kExact, 8>);
       }
       if (rch == 0)
-        snprintf(g_last_variant, sizeof(g_last_variant), "hp<%s,D32,P4,M%d>/smem%dK/%dwarps/%s", dtype_name(dtype), p.M,
-                 p.hp_smem_bytes / 1024, hp_warps, plan.math == kFhfma ? "fhfma" : "exact");
+        snprintf(g_last_variant, sizeof(g_last_variant), "hp<%s,D32,P4,M%d>/smem%dK/%dwarps/%s%s", dtype_name(dtype), p.M,
+                 p.hp_smem_bytes / 1024, hp_warps, plan.math == kFhfma ? "fhfma" : "exact", hp_dyn ? "/dyn" : "");
       return rch;
     }
   }

@@ -141,3 +141,19 @@ def test_head_pair_kernel_non_finite_locations(cuda_device, monkeypatch):
     assert v.startswith("hp<")
     assert not torch.isnan(got).any()
     assert torch.equal(got, want)
+
+
+def test_head_pair_kernel_dynamic_scheduling_is_bit_identical(cuda_device, monkeypatch):
+    """MSDA_B200_HP_DYN=1 (opt-in; measured slower): warps draw (quad, head pair) units from a self-resetting device
+    counter.  Which warp computes a pair does not change its arithmetic; repeated launches re-arm the counter."""
+    monkeypatch.setenv("MSDA_B200_SPLIT", "1")
+    monkeypatch.setenv("MSDA_B200_HP_MIN_QUADS_PER_WARP", "0")
+    inp = _inputs(W.pyramid_shapes(320, 256), 0, 3, seed=17, out_of_range=0.05)
+    d = _dev(inp, torch.float16, cuda_device)
+    want, _ = _run(d, cb.FLAG_NO_SMEM_LEVELS)
+    monkeypatch.setenv("MSDA_B200_HP_SMEM", "0")
+    monkeypatch.setenv("MSDA_B200_HP_DYN", "1")
+    for _ in range(20):
+        got, v = _run(d, 0)
+        assert v.startswith("hp<") and v.endswith("/dyn"), v
+        assert torch.equal(got, want)
