@@ -66,6 +66,7 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the bounded CPU sample")
     ap.add_argument("--no-batch-sweep", action="store_true", help="skip the extra per-GPU batch 2/4/8 rows (N=1 only)")
     ap.add_argument("--no-neighbours", action="store_true", help="skip the extra row for the value_proj tcgen05 kernel (N=1 only)")
+    ap.add_argument("--no-fused-row", action="store_true", help="skip the extra row for the producer-fused entry (N=1 only)")
     ap.add_argument("--no-extra-workloads", action="store_true", help="skip the rows for BASELINE configs[3] (decoder) and configs[4] (1920x1280, plugin path)")
     ap.add_argument("--no-reference-cuda", action="store_true", help="skip timing the reference's CUDA kernel (oracle/_ref) beside ours")
     return ap.parse_args()
@@ -696,6 +697,54 @@ def run_b200(args):
             del sets_b
             torch.cuda.empty_cache()
 
+    # ---- extra row (N=1): the opt-in producer-fused entry (softmax + sampling-location arithmetic in-kernel,
+    # SURVEY 8(f).1) under the same protocol as the headline: rotating cold input sets, CUDA events, its own HBM roofline.
+    # Algorithmic bytes: value + reference points + offsets + logits read once, output written once.
+    fused_row = None
+    if world == 1 and not args.no_fused_row and wl.kind in ("encoder", "decoder"):
+        try:
+            lib = cb._native.load()
+            fsets = []
+            for i in range(n_sets):
+                finp = W.make_inputs(wl, batch=batch, seed=wl.seed + i % 2)
+                cast = lambda a: torch.from_numpy(a).to(device=dev, dtype=dt)
+                fd = {"value": cast(finp.value), "ref": cast(finp.reference_points), "off": cast(finp.sampling_offsets),
+                      "logits": cast(finp.attn_logits), "shapes": torch.from_numpy(finp.spatial_shapes).to(dev),
+                      "starts": torch.from_numpy(finp.level_start_index).to(dev),
+                      "out": torch.empty((batch, dims["Q"], dims["M"] * dims["D"]), dtype=dt, device=dev)}
+                fsets.append(fd)
+            ref_dim = int(fsets[0]["ref"].shape[-1])
+
+            def fused_call(fd):
+                rc = lib.msda_b200_forward_fused(fd["value"].data_ptr(), fd["shapes"].data_ptr(), fd["starts"].data_ptr(), fd["ref"].data_ptr(),
+                                                 fd["off"].data_ptr(), fd["logits"].data_ptr(), fd["out"].data_ptr(), batch, dims["S"], dims["M"],
+                                                 dims["D"], dims["L"], dims["Q"], dims["P"], ref_dim, cb.ops._DTYPES[dt], 0, sptr)
+                assert rc == 0, rc
+            for i in range(5):
+                fused_call(fsets[i % n_sets])
+            torch.cuda.synchronize()
+            f_steps = max(20, min(args.steps, 400))
+            s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s_ev.record(stream)
+            for i in range(f_steps):
+                fused_call(fsets[i % n_sets])
+            e_ev.record(stream)
+            torch.cuda.synchronize()
+            f_us = 1e3 * s_ev.elapsed_time(e_ev) / f_steps
+            f_bytes = esize * batch * (dims["S"] * dims["M"] * dims["D"] + dims["Q"] * dims["L"] * ref_dim
+                                       + 3 * dims["Q"] * dims["M"] * dims["L"] * dims["P"] + dims["Q"] * dims["M"] * dims["D"]) + 24 * dims["L"]
+            peak_f, _ = measured_peaks()
+            fused_row = {"us_per_call": f_us, "images_per_s": batch / (f_us * 1e-6), "kernel": cb.last_variant(), "steps": f_steps,
+                         "roofline": {"bound": "hbm", "achieved": f_bytes / f_us / 1e3, "peak": peak_f, "unit": "GB/s",
+                                      "frac": f_bytes / f_us / 1e3 / peak_f, "algorithmic_bytes_per_launch": f_bytes},
+                         "note": "replaces the caller's softmax + location kernels (17.7 MB written and re-read per image at the headline "
+                                 "shape) at the price of a slower sampling kernel; same rotating cold-input protocol as `value`"}
+            del fsets
+            torch.cuda.empty_cache()
+        except Exception as exc:  # pragma: no cover
+            fused_row = {"error": f"{type(exc).__name__}: {exc}"}
+            torch.cuda.synchronize()
+
     # ---- extra row (N=1, 16-bit only): the producer of `value` (Linear + masked_fill, tcgen05 kernel) ----
     neighbours = None
     if world == 1 and not args.no_neighbours and esize == 2:
@@ -904,7 +953,7 @@ def run_b200(args):
                       "torch_op": "torch.ops.codetr.multi_scale_deformable_attention, back to back"}[args.api],
         },
         "roofline": roofline, "roofline_detail": roofline_detail, "reference_cuda": reference_cuda,
-        "extra_workloads": extra_workloads, "batch_sweep": batch_sweep, "neighbour_kernels": neighbours, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+        "extra_workloads": extra_workloads, "fused_producers": fused_row, "batch_sweep": batch_sweep, "neighbour_kernels": neighbours, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
         "clocks": clocks,
     }
 

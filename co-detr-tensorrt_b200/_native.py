@@ -49,6 +49,9 @@ EXPORTED_SYMBOLS = [
     "msda_b200_algorithmic_hbm_bytes",
     "msda_b200_algorithmic_gather_bytes",
     "msda_b200_read_probe",
+    "msda_b200_packed_value_bytes",
+    "msda_b200_pack_value",
+    "msda_b200_forward_packed",
     "msda_b200_value_proj_supported",
     "msda_b200_value_proj",
     "msda_b200_output_proj",
@@ -188,6 +191,12 @@ def load() -> ctypes.CDLL:
     lib.msda_b200_algorithmic_gather_bytes.argtypes = [i64, i64, i64, i64, i64, i64, ci]
     lib.msda_b200_read_probe.restype = ci
     lib.msda_b200_read_probe.argtypes = [vp, ctypes.c_size_t, ci, vp, vp]
+    lib.msda_b200_packed_value_bytes.restype = ctypes.c_size_t
+    lib.msda_b200_packed_value_bytes.argtypes = [i64, i64, i64, i64, ci]
+    lib.msda_b200_pack_value.restype = ci
+    lib.msda_b200_pack_value.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64, i64, ci, vp]
+    lib.msda_b200_forward_packed.restype = ci
+    lib.msda_b200_forward_packed.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, i64, i64, ci, cu, vp]
     lib.msda_b200_value_proj_supported.restype = ci
     lib.msda_b200_value_proj_supported.argtypes = [i64, i64, ci]
     lib.msda_b200_value_proj.restype = ci

@@ -47,7 +47,10 @@ __device__ __forceinline__ uint4 lds128(unsigned addr) {
 
 // The four samples of one level for this lane group.  `rb` is the lane's row base: a 32-bit shared address
 // (SMEM: cached level, 128-byte pixel pitch) or a 64-bit global address (PIXB-byte pixel pitch).
-template <typename T, int MATH, bool SMEM, int PIXB>
+// PACKED: `vm` points into the pixel-pair packed pyramid (128-byte (pixel, head) entries that also hold the right-hand
+// neighbour, chunk-interleaved; PIXB = M * 128): the two corners of an image row arrive with ONE 32-byte load per lane
+// (LDG.E.256), one L1 wavefront per lane group instead of two.
+template <typename T, int MATH, bool SMEM, int PIXB, bool PACKED = false>
 __device__ __forceinline__ void hp_level_samples(float (&acc)[8], int i00, unsigned pk0, unsigned pk1, const float (&cw)[4], int W,
                                                  const char *vm, unsigned sm_lane) {
   constexpr unsigned group_mask = 0xffffffffu;
@@ -93,7 +96,17 @@ __device__ __forceinline__ void hp_level_samples(float (&acc)[8], int i00, unsig
       else on[j] = bw[j] != 0.f;
     }
     // two row addresses per sample (top-left, bottom-left); the right-hand corners are immediate offsets
-    if constexpr (SMEM) {
+    if constexpr (PACKED) {
+      const char *g0 = vm + (ptrdiff_t)bi * (ptrdiff_t)PIXB;
+      const char *g1 = vm + (ptrdiff_t)(bi + W) * (ptrdiff_t)PIXB;
+      U8 top, bot;
+      if (on[0] || on[1]) top = ldg256(g0);
+      if (on[2] || on[3]) bot = ldg256(g1);
+      rows[0] = make_uint4(top.v[0], top.v[1], top.v[2], top.v[3]);
+      rows[1] = make_uint4(top.v[4], top.v[5], top.v[6], top.v[7]);
+      rows[2] = make_uint4(bot.v[0], bot.v[1], bot.v[2], bot.v[3]);
+      rows[3] = make_uint4(bot.v[4], bot.v[5], bot.v[6], bot.v[7]);
+    } else if constexpr (SMEM) {
       const unsigned s0 = sm_lane + (unsigned)bi * 128u, s1 = s0 + (unsigned)W * 128u;
       if (on[0]) rows[0] = lds128(s0);
       if (on[1]) rows[1] = lds128(s0 + 128u);
@@ -120,10 +133,35 @@ __device__ __forceinline__ void hp_level_samples(float (&acc)[8], int i00, unsig
   }
 }
 
+// Geometry for the packed pyramid: like make_geo(), but the index names the ENTRY that holds the sample's two upper
+// corners.  Column -1 (only the right-hand corners are inside): the entry of column 0 is used and its LEFT half is the
+// sample's right-hand corner, so the weight pair is (lw, 0) instead of (0, lw) -- the same products in the same order.
+__device__ __forceinline__ void make_geo_packed(float x, float y, float aw, int H, int W, int &e_top, float (&cw)[4]) {
+  const float w_im = __fmul_rn(x, (float)W) - 0.5f;
+  const float h_im = __fmul_rn(y, (float)H) - 0.5f;
+  const bool inside = (h_im > -1.f) && (w_im > -1.f) && (h_im < (float)H) && (w_im < (float)W);
+  const float hf = floorf(h_im), wf = floorf(w_im);
+  const int h_lo = (int)hf, w_lo = (int)wf;
+  const float lh = h_im - hf, lw = w_im - wf;
+  const float hh = 1.f - lh, hw = 1.f - lw;
+  const float wy0 = (inside && h_lo >= 0) ? hh * aw : 0.f;
+  const float wy1 = (inside && h_lo < H - 1) ? lh * aw : 0.f;
+  const bool neg = w_lo < 0;
+  const float wl = inside ? (neg ? lw : hw) : 0.f;
+  const float wr = (inside && !neg && w_lo < W - 1) ? lw : 0.f;
+  cw[0] = wy0 * wl;
+  cw[1] = wy0 * wr;
+  cw[2] = wy1 * wl;
+  cw[3] = wy1 * wr;
+  e_top = h_lo * W + (neg ? 0 : w_lo);
+}
+
 // T: __half / __nv_bfloat16, D = 32, P = 4, MT heads (compile time: the neighbour-pixel offset is an immediate).
 // DYN: warps draw (query quad, head pair) units from the launch's device counter instead of striding over their own
 // head pair's quads (no cached levels in that mode: a CTA is no longer tied to one head pair).
-template <typename T, int MATH, int MT, bool DYN = false>
+// PACKED: `p.packed` holds the pixel-pair packed pyramid (written by msda_pack_value or by the projection kernel's
+// epilogue); `p.value` is not read.  No cached levels in that mode.
+template <typename T, int MATH, int MT, bool DYN = false, bool PACKED = false>
 __global__ void __launch_bounds__(kHpThreads, 1) msda_fwd_hp(const MsdaParams p) {
   constexpr int D = 32, E = 2, VEC = 8;
   extern __shared__ __align__(128) unsigned char hp_rows[];  // cached levels: [pixel][2 heads][64 B]
@@ -139,8 +177,8 @@ __global__ void __launch_bounds__(kHpThreads, 1) msda_fwd_hp(const MsdaParams p)
   const int rank = (int)blockIdx.x / NG;      // this CTA among those of the head pair
   const int cpg = (int)gridDim.x / NG;        // CTAs per head pair (the host launches a multiple of NG)
   const int b = blockIdx.y;
-  const unsigned pix_bytes = (unsigned)(M * D * E);
-  const char *__restrict__ value = static_cast<const char *>(p.value);
+  const unsigned pix_bytes = (unsigned)(M * D * E) * (PACKED ? 2u : 1u);  // packed entries are 128 bytes per head
+  const char *__restrict__ value = static_cast<const char *>(PACKED ? p.packed : p.value);
   const T *__restrict__ loc = static_cast<const T *>(p.loc);
   const T *__restrict__ wgt = static_cast<const T *>(p.weight);
   T *__restrict__ out = static_cast<T *>(p.out);
@@ -159,7 +197,7 @@ __global__ void __launch_bounds__(kHpThreads, 1) msda_fwd_hp(const MsdaParams p)
     int l0 = p.L;
     for (int l = p.L - 1; l >= 0; --l) {
       const long long n = (long long)lv[l].H * lv[l].W;
-      const bool ok = lv[l].H > 0 && lv[l].W > 0 && lv[l].start >= 0 && (long long)lv[l].start + n <= (long long)p.S &&
+      const bool ok = !PACKED && lv[l].H > 0 && lv[l].W > 0 && lv[l].start >= 0 && (long long)lv[l].start + n <= (long long)p.S &&
                       used + n * 128 <= (long long)p.hp_smem_bytes;
       if (!ok) break;
       used += n * 128;
@@ -196,7 +234,8 @@ __global__ void __launch_bounds__(kHpThreads, 1) msda_fwd_hp(const MsdaParams p)
   const int units = (p.Q + 3) >> 2;
   const int nw = (int)blockDim.x >> 5;  // warps per CTA: chosen by the host so that the units divide evenly
   const int stride = cpg * nw;
-  const char *vm_img = value + (size_t)b * p.S * M * (size_t)(D * E) + (size_t)sub * 16;  // head 0 of this image, this lane's 16 bytes
+  constexpr int kHeadBytes = D * E * (PACKED ? 2 : 1), kLaneBytes = PACKED ? 32 : 16;
+  const char *vm_img = value + (size_t)b * p.S * M * (size_t)kHeadBytes + (size_t)sub * kLaneBytes;  // head 0 of this image, this lane's bytes
   const unsigned sm_lane = smem_u32(hp_rows) + (unsigned)(hh * 64 + sub * 16);
 
   // Per-image bases are uniform; inside an image this lane's next sample is addressed by ONE running 32-bit byte
@@ -240,7 +279,8 @@ __global__ void __launch_bounds__(kHpThreads, 1) msda_fwd_hp(const MsdaParams p)
     float x, y, aw;
     decode_raw<T>(rw, x, y, aw);
     aw = lv_live ? aw : 0.f;
-    make_geo(x, y, aw, H, g.W, g.i00, g.cw);
+    if constexpr (PACKED) make_geo_packed(x, y, aw, H, g.W, g.i00, g.cw);
+    else make_geo(x, y, aw, H, g.W, g.i00, g.cw);
     g.i00 += lv[l].base;
     g.pk0 = g.pk1 = 0u;
     if constexpr (MATH == kFhfma) {
@@ -272,7 +312,7 @@ __global__ void __launch_bounds__(kHpThreads, 1) msda_fwd_hp(const MsdaParams p)
     cur = first + warp;
     nxt = cur + stride;
   }
-  const char *vm = vm_img + (size_t)unit_head(cur) * (size_t)(D * E);
+  const char *vm = vm_img + (size_t)unit_head(cur) * (size_t)kHeadBytes;
   asm volatile("" : "+l"(vm));  // one opaque 64-bit base: every corner address is a single IMAD.WIDE
 
   unsigned off = unit_offset(cur);          // offset of the inputs held in `raw`
@@ -299,7 +339,7 @@ __global__ void __launch_bounds__(kHpThreads, 1) msda_fwd_hp(const MsdaParams p)
       const Geo next = geometry(raw, wrap ? 0 : l + 1, wrap ? live_n : live);
       off = (l + 2 == p.L) ? unit_offset(nxt) : off + 16u;
       raw = load_sample(off);
-      hp_level_samples<T, MATH, kSmem, MT * D * E>(acc, geo.i00, geo.pk0, geo.pk1, geo.cw, geo.W, vm, sm_lane);
+      hp_level_samples<T, MATH, kSmem, MT * D * E * (PACKED ? 2 : 1), PACKED>(acc, geo.i00, geo.pk0, geo.pk1, geo.cw, geo.W, vm, sm_lane);
       geo = next;
     };
     // fine levels from global memory, then the cached coarse levels from shared memory
@@ -313,7 +353,7 @@ __global__ void __launch_bounds__(kHpThreads, 1) msda_fwd_hp(const MsdaParams p)
     cur = nxt;
     nxt = after;
     if constexpr (DYN) {
-      vm = vm_img + (size_t)unit_head(cur) * (size_t)(D * E);
+      vm = vm_img + (size_t)unit_head(cur) * (size_t)kHeadBytes;
       asm volatile("" : "+l"(vm));
     }
     ++it;

@@ -1459,8 +1459,6 @@ __global__ void __launch_bounds__(kSmallThreads, 8) msda_fwd_small(const MsdaPar
   if (live && split == 0) store_row<T, VEC>(out + pair * D + sub * VEC, acc);
 }
 
-#include "msda_fwd_hp.cuh"
-
 // ---------------------------------------------------------------------------
 // Packed path (16-bit types, D = 32, P = 4): pixel-pair packed pyramid + 256-bit loads.
 //
@@ -1685,6 +1683,8 @@ __global__ void __launch_bounds__(kThreads, MSDA_MINB) msda_fwd_packed(const Msd
     if (live) store_row<T, 8>(out + pair * D + sub * 8, acc);
   }
 }
+
+#include "msda_fwd_hp.cuh"
 
 // ---------------------------------------------------------------------------
 // Backward: gradients w.r.t. value (scatter-add with atomics, like the
@@ -2112,6 +2112,26 @@ int run_generic(const MsdaParams &p, int dtype, cudaStream_t stream) {
   return rc;
 }
 
+// Warps per CTA of the head-pair kernel: every warp of the cpg CTAs of a head pair walks the query quads with one stride,
+// so a call takes ceil(quads / (cpg * nw)) rounds; pick the nw that wastes the least of the last round -- 4,604 quads over
+// 37 CTAs: 24 warps -> 6 rounds, 86 % busy; 25 warps -> 5 rounds, 99.5 %.  Fewer warps hide less latency: a configuration
+// with half the warps must be 14 % better balanced to win.
+int hp_pick_warps(int64_t quads, int cpg) {
+  int pick = kHpThreads / 32;
+  double best = -1.0;
+  for (int nw = kHpThreads / 32; nw >= kHpThreads / 64 && cpg > 0; --nw) {
+    const int64_t per_round = (int64_t)cpg * nw;
+    const int64_t rounds = (quads + per_round - 1) / per_round;
+    const double eff = rounds > 0 ? (double)quads / (double)(rounds * per_round) : 0.0;
+    const double score = eff * (0.75 + 0.25 * (double)nw / (double)(kHpThreads / 32));
+    if (score > best + 1e-4) {
+      best = score;
+      pick = nw;
+    }
+  }
+  return pick;
+}
+
 bool aligned_to(const void *ptr, size_t a) { return (reinterpret_cast<uintptr_t>(ptr) % a) == 0; }
 
 // Bytes of workspace the packed path needs, or 0 when it does not apply / would not pay off: 16-bit
@@ -2318,20 +2338,8 @@ int forward_impl(MsdaParams p, int dtype, unsigned flags, void *workspace, size_
     // call takes ceil(quads / (cpg * nw)) rounds; pick the nw (of the upper half of what the register budget
     // allows) that wastes the least of the last round -- 4,604 quads over 37 CTAs: 24 warps -> 6 rounds, 86 %
     // busy; 25 warps -> 5 rounds, 99.5 %.
-    int hp_warps = kHpThreads / 32;
+    int hp_warps = hp_pick_warps(quads, cpg);
     {
-      double best = -1.0;
-      for (int nw = kHpThreads / 32; nw >= kHpThreads / 64 && cpg > 0; --nw) {
-        const int64_t per_round = (int64_t)cpg * nw;
-        const int64_t rounds = (quads + per_round - 1) / per_round;
-        const double eff = rounds > 0 ? (double)quads / (double)(rounds * per_round) : 0.0;
-        // fewer warps hide less latency: a configuration with half the warps must be 14 % better balanced to win
-        const double score = eff * (0.75 + 0.25 * (double)nw / (double)(kHpThreads / 32));
-        if (score > best + 1e-4) {
-          best = score;
-          hp_warps = nw;
-        }
-      }
       hp_warps = env_int("MSDA_B200_HP_WARPS", hp_warps);
       if (hp_warps < 1) hp_warps = 1;
       if (hp_warps > kHpThreads / 32) hp_warps = kHpThreads / 32;
@@ -2710,6 +2718,85 @@ int msda_b200_backward(const void *value, const int64_t *spatial_shapes, const i
   }
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return (int)cudaGetLastError();
+}
+
+size_t msda_b200_packed_value_bytes(int64_t batch, int64_t num_keys, int64_t num_heads, int64_t channels, int dtype) {
+  if ((dtype != MSDA_F16 && dtype != MSDA_BF16) || channels != 32 || batch <= 0 || num_keys <= 0 || num_heads <= 0) return 0;
+  return (size_t)batch * (size_t)num_keys * (size_t)num_heads * 128;
+}
+
+int msda_b200_pack_value(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index, void *packed,
+                         int64_t batch, int64_t num_keys, int64_t num_heads, int64_t channels, int64_t num_levels, int dtype,
+                         void *stream_v) {
+  if (msda_b200_packed_value_bytes(batch, num_keys, num_heads, channels, dtype) == 0 || num_levels <= 0 || num_levels > kMaxLevelsSmem)
+    return MSDA_ERR_UNSUPPORTED;
+  if (!value || !spatial_shapes || !level_start_index || !packed) return MSDA_ERR_NULL_POINTER;
+  if (!aligned_to(value, 16) || !aligned_to(packed, 32)) return MSDA_ERR_MISALIGNED;
+  MsdaParams p;
+  memset(&p, 0, sizeof(p));
+  p.value = value; p.shapes = spatial_shapes; p.starts = level_start_index; p.packed = packed;
+  p.B = (int)batch; p.S = (int)num_keys; p.M = (int)num_heads; p.D = (int)channels; p.L = (int)num_levels;
+  p.tile_w_log2 = 3; p.tile_h_log2 = 2; p.want_tiled = 0; p.Q = (int)num_keys; p.P = 4;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  const long long chunks = (long long)batch * num_keys * num_heads * 4;
+  long long grid = (chunks + kThreads - 1) / kThreads;
+  const long long cap = (long long)sm_count() * 16;
+  if (grid > cap) grid = cap;
+  if (dtype == MSDA_F16) msda_pack_value<__half><<<(unsigned)grid, kThreads, 0, stream>>>(p);
+  else msda_pack_value<__nv_bfloat16><<<(unsigned)grid, kThreads, 0, stream>>>(p);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  const int rc = (int)cudaGetLastError();
+  if (rc == 0) snprintf(g_last_variant, sizeof(g_last_variant), "pack_value<%s>", dtype_name(dtype));
+  return rc;
+}
+
+int msda_b200_forward_packed(const void *packed_value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                             const void *sampling_loc, const void *attn_weight, void *output, int64_t batch, int64_t num_keys,
+                             int64_t num_heads, int64_t channels, int64_t num_levels, int64_t num_queries, int64_t num_points,
+                             int dtype, unsigned flags, void *stream_v) {
+  if ((flags & MSDA_FLAG_MATH_FHFMA) && (flags & MSDA_FLAG_MATH_EXACT)) return MSDA_ERR_BAD_FLAGS;
+  if (batch < 0 || num_keys < 0 || num_queries < 0) return MSDA_ERR_BAD_SHAPE;
+  if (batch * num_queries == 0) return MSDA_OK;
+  // what the packed gather is written for; anything else goes through msda_b200_forward on the plain layout
+  if ((dtype != MSDA_F16 && dtype != MSDA_BF16) || channels != 32 || num_heads != 8 || num_points != 4 || num_levels < 2 ||
+      num_levels > kHpMaxLevels || batch > 65535 || (int64_t)num_queries * num_heads * num_levels * 16 >= ((int64_t)1 << 32) ||
+      num_keys >= ((int64_t)1 << 31) / 1024)
+    return MSDA_ERR_UNSUPPORTED;
+  if (!packed_value || !spatial_shapes || !level_start_index || !sampling_loc || !attn_weight || !output) return MSDA_ERR_NULL_POINTER;
+  if (!aligned_to(packed_value, 32) || !aligned_to(output, 16) || !aligned_to(sampling_loc, 4) || !aligned_to(attn_weight, 2) ||
+      !aligned_to(spatial_shapes, 8) || !aligned_to(level_start_index, 8))
+    return MSDA_ERR_MISALIGNED;
+  MsdaParams p;
+  memset(&p, 0, sizeof(p));
+  p.packed = const_cast<void *>(packed_value);
+  p.shapes = spatial_shapes; p.starts = level_start_index; p.loc = sampling_loc; p.weight = attn_weight; p.out = output;
+  p.B = (int)batch; p.S = (int)num_keys; p.M = (int)num_heads; p.D = (int)channels; p.L = (int)num_levels;
+  p.Q = (int)num_queries; p.P = (int)num_points;
+  int math = (dtype == MSDA_F16) ? kFhfma : kExact;
+  if (flags & MSDA_FLAG_MATH_FHFMA) math = kFhfma;
+  if (flags & MSDA_FLAG_MATH_EXACT) math = kExact;
+  const int sms = sm_count(), NG = 4, cpg = sms / NG;
+  if (cpg < 1) return MSDA_ERR_UNSUPPORTED;
+  const int64_t quads = (num_queries + 3) / 4;
+  int warps = env_int("MSDA_B200_HP_WARPS", hp_pick_warps(quads, cpg));
+  if (warps < 1 || warps > kHpThreads / 32) warps = kHpThreads / 32;
+  const bool pdl = env_int("MSDA_B200_PDL", 1) != 0;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  const dim3 grid((unsigned)(cpg * NG), (unsigned)batch, 1), block((unsigned)warps * 32u);
+  cudaError_t le;
+  if (dtype == MSDA_F16) {
+    le = math == kFhfma ? launch_kernel(msda_fwd_hp<__half, kFhfma, 8, false, true>, grid, block, 0, stream, pdl, p)
+                        : launch_kernel(msda_fwd_hp<__half, kExact, 8, false, true>, grid, block, 0, stream, pdl, p);
+  } else {
+    le = math == kFhfma ? launch_kernel(msda_fwd_hp<__nv_bfloat16, kFhfma, 8, false, true>, grid, block, 0, stream, pdl, p)
+                        : launch_kernel(msda_fwd_hp<__nv_bfloat16, kExact, 8, false, true>, grid, block, 0, stream, pdl, p);
+  }
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  const int rc = le != cudaSuccess ? (int)le : (int)cudaGetLastError();
+  if (rc == 0)
+    snprintf(g_last_variant, sizeof(g_last_variant), "hp_packed<%s,D32,P4,M8>/%dwarps/%s", dtype_name(dtype), warps,
+             math == kFhfma ? "fhfma" : "exact");
+  return rc;
 }
 
 int msda_b200_read_probe(const void *buf, size_t bytes, int repeats, void *sink, void *stream) {

@@ -361,6 +361,48 @@ def output_proj(attended: Tensor, weight: Tensor, bias: Optional[Tensor], residu
     return out
 
 
+def pack_value(value: Tensor, spatial_shapes: Tensor, level_start_index: Tensor) -> Tensor:
+    """Plain ``[bs, S, M, 32]`` 16-bit value tensor -> pixel-pair packed pyramid (``msda_b200_pack_value``): a uint8
+    tensor of ``bs * S * M * 128`` bytes for :func:`forward_packed`.  The projection kernel can write this layout
+    directly (``value_proj(..., packed=True)``), which is the point; this pre-pass exists for callers that already
+    hold a plain tensor and for tests."""
+    _require(value.is_cuda and value.is_contiguous() and value.dim() == 4, "value has to be a contiguous CUDA tensor [bs, S, M, D]")
+    _require(value.dtype in (torch.float16, torch.bfloat16) and value.shape[3] == 32, "packed layout: fp16 / bf16, D = 32")
+    bs, keys, heads, chans = value.shape
+    need = int(_lib.msda_b200_packed_value_bytes(bs, keys, heads, chans, _DTYPES[value.dtype]))
+    _require(need > 0, "no packed form for this shape")
+    packed = torch.empty(need, dtype=torch.uint8, device=value.device)
+    with torch.cuda.device(value.device):
+        _check(_lib.msda_b200_pack_value(value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), packed.data_ptr(),
+                                         bs, keys, heads, chans, spatial_shapes.shape[0], _DTYPES[value.dtype],
+                                         _stream_ptr(value.device, None)))
+    return packed
+
+
+def forward_packed(packed_value: Tensor, dtype: torch.dtype, num_keys: int, spatial_shapes: Tensor, level_start_index: Tensor,
+                   sampling_loc: Tensor, attn_weight: Tensor, flags: Optional[int] = None, out: Optional[Tensor] = None) -> Tensor:
+    """The operator on a packed value pyramid (``msda_b200_forward_packed``): same ``sampling_loc`` / ``attn_weight`` /
+    output contract and the same bits as the op on the plain tensor.  ``packed_value``: uint8 buffer from
+    :func:`pack_value` or ``value_proj(..., packed=True)``; ``dtype`` the element type it holds; 8 heads x 32 channels."""
+    _require(packed_value.is_cuda and packed_value.is_contiguous() and packed_value.dtype == torch.uint8, "packed_value: contiguous CUDA uint8 buffer")
+    for name, t in (("sampling_loc", sampling_loc), ("attn_weight", attn_weight), ("spatial_shapes", spatial_shapes),
+                    ("level_start_index", level_start_index)):
+        _require(t.is_contiguous() and t.is_cuda and t.device == packed_value.device, f"{name} must be a contiguous CUDA tensor on the value's device")
+    _require(sampling_loc.dim() == 6 and attn_weight.dim() == 5 and sampling_loc.dtype == attn_weight.dtype == dtype, "bad sampling_loc / attn_weight")
+    bs, queries, heads, levels, points, _ = sampling_loc.shape
+    _require(tuple(attn_weight.shape) == (bs, queries, heads, levels, points), "attn_weight shape mismatch")
+    _require(packed_value.numel() == bs * int(num_keys) * heads * 128, "packed_value size does not match bs * num_keys * heads * 128")
+    if out is None:
+        out = torch.empty((bs, queries, heads * 32), dtype=dtype, device=packed_value.device)
+    with torch.cuda.device(packed_value.device):
+        rc = _lib.msda_b200_forward_packed(packed_value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+                                           sampling_loc.data_ptr(), attn_weight.data_ptr(), out.data_ptr(), bs, int(num_keys), heads, 32,
+                                           levels, queries, points, _DTYPES[dtype], _default_flags if flags is None else int(flags),
+                                           _stream_ptr(packed_value.device, None))
+    _check(rc)
+    return out
+
+
 def plugin_enqueue(
     value_dims: Sequence[int],
     loc_dims: Sequence[int],

@@ -201,6 +201,34 @@ int msda_b200_backward(const void *value, const int64_t *spatial_shapes, const i
                        int64_t num_queries, int64_t num_points, int64_t im2col_step, int dtype,
                        unsigned flags, void *stream);
 
+/*
+ * Packed value pyramid ("emit the layout the kernel prefers").  No reference counterpart: the
+ * reference's module hands the op the plain [B, S, M, D] tensor (multi_scale_deformable_attention.py:173-176).
+ *
+ * Layout: one 128-byte, line-aligned entry per (key s, head m) at byte offset ((b*S + s)*M + m)*128, holding the key's
+ * 64-byte row AND the row of the key to its right in the flattened pyramid (s + 1), interleaved in 16-byte chunks:
+ *     [ v(s)[0:8] | v(s+1)[0:8] | v(s)[8:16] | v(s+1)[8:16] | v(s)[16:24] | v(s+1)[16:24] | v(s)[24:32] | v(s+1)[24:32] ]
+ * so the two horizontal corners of a bilinear sample arrive with one 32-byte load per lane and one L1 wavefront per lane
+ * group instead of two.  The right-hand half of the last key of an image row is never used (its weight is zero), so a
+ * producer may leave anything there.  16-bit types, channels == 32 only.
+ *
+ *   msda_b200_packed_value_bytes   size of the packed buffer, or 0 when the shape / dtype has no packed form
+ *   msda_b200_pack_value           plain value tensor -> packed buffer (a pre-pass; the projection kernel below can write
+ *                                  the packed layout directly instead: msda_b200_value_proj with `packed_out`)
+ *   msda_b200_forward_packed       the operator on a packed value buffer: same sampling_loc / attn_weight / output
+ *                                  contract and the same bits as msda_b200_forward on the plain tensor.  num_heads == 8,
+ *                                  num_points == 4, 2 <= num_levels <= 8, else MSDA_ERR_UNSUPPORTED (the caller keeps
+ *                                  the plain path).  `packed_value` 32-byte aligned.
+ */
+size_t msda_b200_packed_value_bytes(int64_t batch, int64_t num_keys, int64_t num_heads, int64_t channels, int dtype);
+int msda_b200_pack_value(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index, void *packed,
+                         int64_t batch, int64_t num_keys, int64_t num_heads, int64_t channels, int64_t num_levels, int dtype,
+                         void *stream);
+int msda_b200_forward_packed(const void *packed_value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                             const void *sampling_loc, const void *attn_weight, void *output, int64_t batch,
+                             int64_t num_keys, int64_t num_heads, int64_t channels, int64_t num_levels, int64_t num_queries,
+                             int64_t num_points, int dtype, unsigned flags, void *stream);
+
 /* ---- introspection / measurement helpers (no reference counterpart) ---- */
 
 /* ABI version of the loaded library (== MSDA_B200_ABI_VERSION). */

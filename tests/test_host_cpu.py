@@ -296,3 +296,34 @@ def test_registered_overload_is_what_the_dynamo_converter_keys_on():
     assert not any(a.alias_info is not None and a.alias_info.is_write for a in schema.arguments)   # functional: safe to trace
     bwd = torch.ops.codetr.multi_scale_deformable_attention_backward.default._schema
     assert [str(a.type) for a in bwd.arguments] == ["Tensor"] * 9 + ["int"]
+
+
+def test_bench_roofline_helpers_recompute_from_committed_files():
+    """Every floor of bench.py's `roofline_detail` must be recomputable from files under profiles/: the committed ncu
+    counters of the headline configuration, the gather probe's ceilings, and the live-row count of the inputs."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("_bench_under_test", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    c = bench.committed_counters("swinl_enc_1152x768", "float16", 1)
+    assert c and c["dram_bytes"] > 20e6 and c["lts_read_sectors"] > 1e6 and c["l1_wavefronts"] > 1e6
+    assert c["source"].startswith("profiles/") and os.path.isfile(os.path.join(ROOT, c["source"].split(" ")[0]))
+    ceil = bench.gather_probe_ceiling()
+    assert ceil and 0.9 < ceil["ldg128_rows_per_clk_per_sm"] < 1.3 and 1.7 < ceil["lds128_rows_per_clk_per_sm"] <= 2.0
+    # live corner rows: brute force on a small pyramid against the helper
+    wl = W.Workload(name="t", shapes=((6, 9), (3, 5)), num_queries=0, batch=1, kind="encoder", seed=2)
+    inp = W.make_inputs(wl, out_of_range_frac=0.2)
+    want = 0
+    loc = inp.sampling_loc.astype(np.float32)
+    for l, (H, Wd) in enumerate(inp.spatial_shapes):
+        for x, y in loc[..., l, :, :].reshape(-1, 2):
+            xi, yi = np.float32(x) * np.float32(Wd) - np.float32(0.5), np.float32(y) * np.float32(H) - np.float32(0.5)
+            if not (xi > -1 and xi < Wd and yi > -1 and yi < H):
+                continue
+            x0, y0 = int(np.floor(xi)), int(np.floor(yi))
+            want += sum(1 for dx in (0, 1) for dy in (0, 1) if 0 <= x0 + dx <= Wd - 1 and 0 <= y0 + dy <= H - 1)
+    assert bench.live_corner_rows(inp) == want > 0
+    # the reference arm's workload loader does not import the package
+    mod = bench.load_workloads_standalone()
+    assert mod.CONFIGS["swinl_enc_1152x768"].Q == 18414 and mod.__name__ == "_msda_workloads_standalone"

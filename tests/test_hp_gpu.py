@@ -157,3 +157,28 @@ def test_head_pair_kernel_dynamic_scheduling_is_bit_identical(cuda_device, monke
         got, v = _run(d, 0)
         assert v.startswith("hp<") and v.endswith("/dyn"), v
         assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("dt", ["f16", "bf16"])
+def test_packed_value_pyramid_gather_is_bit_identical(dt, cuda_device, monkeypatch):
+    """msda_b200_pack_value + msda_b200_forward_packed (pixel-pair packed pyramid, one 32-byte load per lane for the two
+    corners of an image row -- measured no faster, kept as a documented experiment): the same bits as the op on the
+    plain tensor, including the column -1 / last column / first row / last row cases of a 5 %-out-of-range input."""
+    monkeypatch.setenv("MSDA_B200_SPLIT", "1")
+    for shapes, Q, B in ((W.pyramid_shapes(320, 256), 0, 2), (((40, 60), (20, 30), (10, 15)), 2501, 1)):
+        inp = _inputs(shapes, Q, B, seed=23, out_of_range=0.05, kind="encoder" if Q == 0 else "decoder")
+        d = _dev(inp, DT[dt], cuda_device)
+        for fl in (0, cb.FLAG_MATH_EXACT, cb.FLAG_MATH_FHFMA):
+            want, _ = _run(d, fl | cb.FLAG_NO_SMEM_LEVELS)
+            packed = cb.pack_value(d["value"], d["spatial_shapes"], d["level_start_index"])
+            assert packed.numel() == d["value"].numel() * 4          # 128 bytes per (key, head): twice the plain tensor
+            before = cb.launch_count()
+            got = cb.forward_packed(packed, DT[dt], d["value"].shape[1], d["spatial_shapes"], d["level_start_index"],
+                                    d["sampling_loc"], d["attn_weight"], flags=fl)
+            torch.cuda.synchronize()
+            assert cb.launch_count() == before + 1 and cb.last_variant().startswith("hp_packed<")
+            assert torch.equal(got, want)
+    # shapes the packed gather is not written for are refused, not mis-computed
+    with pytest.raises(RuntimeError):
+        cb.forward_packed(packed, DT[dt], d["value"].shape[1], d["spatial_shapes"][:1].contiguous(), d["level_start_index"][:1].contiguous(),
+                          d["sampling_loc"][:, :, :, :1].contiguous(), d["attn_weight"][:, :, :, :1].contiguous())
