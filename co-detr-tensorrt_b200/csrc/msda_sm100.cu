@@ -2330,7 +2330,9 @@ int forward_impl(MsdaParams p, int dtype, unsigned flags, void *workspace, size_
                           // exact-arithmetic calls (bf16 default, MSDA_FLAG_MATH_EXACT) stay on the vector kernel, which is
                           // 3 % faster for them at the headline shape (58.9 vs 60.6 us); MSDA_B200_HP_EXACT=1 overrides
                           (plan.math == kFhfma || env_int("MSDA_B200_HP_EXACT", 0)) &&
-                          aligned_to(p.loc, 4) && !(flags & MSDA_FLAG_NO_SMEM_LEVELS);
+                          aligned_to(p.loc, 4) && !(flags & MSDA_FLAG_NO_SMEM_LEVELS) &&
+                          // the kernel addresses an image's locations with 32-bit byte offsets
+                          (int64_t)p.Q * p.M * p.L * 16 < ((int64_t)1 << 32);
     const int cpg = NG > 0 ? sms / NG : 0;
     const int64_t quads = ((int64_t)p.Q + 3) / 4;
     const int64_t hp_min_quads = (int64_t)env_int("MSDA_B200_HP_MIN_QUADS_PER_WARP", 2) * cpg * (kHpThreads / 32);
