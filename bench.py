@@ -831,10 +831,14 @@ def run_b200(args):
                 dist.all_reduce(ms, op=dist.ReduceOp.MAX)
             return float(ms.item()) / steps_x, 1e6 * host_s / steps_x
 
-        for xname, xbatch, xapis in (("swinl_dec_1152x768", 1, ("cabi", "cuda_graph", "torch_op")), ("swinl_enc_1920x1280", 2, ("plugin",))):
+        # ... and the headline shape in the other two element types the plugin accepts (bf16, fp32), same kernel family
+        for xname, xbatch, xapis, xdtype in (("swinl_dec_1152x768", 1, ("cabi", "cuda_graph", "torch_op"), None),
+                                             ("swinl_enc_1920x1280", 2, ("plugin",), None),
+                                             ("swinl_enc_1152x768", 1, ("cabi",), "bfloat16"), ("swinl_enc_1152x768", 1, ("cabi",), "float32")):
+            xkey = xname if xdtype is None else f"{xname}/{xdtype}"
             try:
                 xwl = W.CONFIGS[xname]
-                xdt = torch_dtype(xwl.dtype)
+                xdt = torch_dtype(xdtype or xwl.dtype)
                 xes = torch.empty((), dtype=xdt).element_size()
                 xhbm = W.algorithmic_hbm_bytes(xwl, xbatch, xes)
                 xn = min(16, max(2, -(-int(1.5 * L2_BYTES) // xhbm)))
@@ -847,7 +851,7 @@ def run_b200(args):
                         xd[k] = t.to(dev) if t.dtype == torch.int64 else t.to(device=dev, dtype=xdt)
                     xsets.append(xd)
                 xdims = {**xwl.dims(), "B": xbatch}
-                row = {"per_gpu_batch": xbatch, **xdims, "dtype": xwl.dtype, "note": xwl.note,
+                row = {"per_gpu_batch": xbatch, **xdims, "dtype": xdtype or xwl.dtype, "note": xwl.note,
                        "l2_policy": f"rotating {xn} distinct device input sets ({xn * xhbm / 1e6:.0f} MB)", "apis": {}}
                 xsteps = max(50, min(args.steps, 400))
                 for api in xapis:
@@ -871,11 +875,11 @@ def run_b200(args):
                     row["apis"][api] = {"us_per_call": ms * 1e3, "images_per_s": world * xbatch / (ms * 1e-3),
                                         "host_us_per_call": None if api == "cuda_graph" else host_us,
                                         "hbm_frac": xhbm / (ms * 1e-3) / 1e9 / peak_hbm, "kernel": cb.last_variant(), "steps": xsteps}
-                extra_workloads[xname] = row
+                extra_workloads[xkey] = row
                 del xsets
                 torch.cuda.empty_cache()
             except Exception as exc:  # pragma: no cover
-                extra_workloads[xname] = {"error": f"{type(exc).__name__}: {exc}"}
+                extra_workloads[xkey] = {"error": f"{type(exc).__name__}: {exc}"}
                 torch.cuda.synchronize()
 
     # L2 -> SM read bandwidth of this GPU, measured live with the library's read probe (48 MB working set, L2-resident)

@@ -50,10 +50,18 @@ __device__ __forceinline__ uint4 lds128(unsigned addr) {
 // PACKED: `vm` points into the pixel-pair packed pyramid (128-byte (pixel, head) entries that also hold the right-hand
 // neighbour, chunk-interleaved; PIXB = M * 128): the two corners of an image row arrive with ONE 32-byte load per lane
 // (LDG.E.256), one L1 wavefront per lane group instead of two.
+// MATH = kFhfmaSplit (bf16): FHFMA with every corner weight as TWO bf16 terms, w = hi + lo (|w - hi - lo| <= 2^-17 |w|):
+// the 8-bit bf16 weight alone costs 2^-9 per product, past the one-output-rounding gate, while the exact path spends
+// 12 instructions per corner row (8 integer unpacks + 4 FFMA2) and four fp32 weight registers per sample.
+constexpr int kFhfmaSplit = 2;
+
 template <typename T, int MATH, bool SMEM, int PIXB, bool PACKED = false>
-__device__ __forceinline__ void hp_level_samples(float (&acc)[8], int i00, unsigned pk0, unsigned pk1, const float (&cw)[4], int W,
-                                                 const char *vm, unsigned sm_lane) {
+__device__ __forceinline__ void hp_level_samples(float (&acc)[16 / sizeof(T)], int i00, unsigned pk0, unsigned pk1, unsigned pk2, unsigned pk3,
+                                                 const float (&cw)[4], int W, const char *vm, unsigned sm_lane) {
+  constexpr bool kPackedW = MATH == kFhfma || MATH == kFhfmaSplit;  // corner weights travel as packed 16-bit pairs
   constexpr unsigned group_mask = 0xffffffffu;
+  constexpr int G = 32 * (int)sizeof(T) / 16;   // lanes per corner row: 4 (16-bit), 8 (fp32: a row is a whole 128-byte line)
+  constexpr unsigned SPIX = 64u * (unsigned)sizeof(T);  // bytes per pixel of a cached level: two heads x 32 channels
   // The broadcasts of sample k + MSDA_HP_BCAST_AHEAD can be written ahead of sample k's loads (the ncu source view
   // shows 14 % of the stall samples on the predicate tests waiting for their shuffle).  Measured at the headline shape:
   // 0 / 1 / 2 / 4 samples ahead = 44.59 / 44.59 / 44.91 / 44.96 us -- ptxas schedules the shuffles itself; default 0.
@@ -61,16 +69,20 @@ __device__ __forceinline__ void hp_level_samples(float (&acc)[8], int i00, unsig
 #define MSDA_HP_BCAST_AHEAD 0
 #endif
   int bis[4];
-  unsigned bp0s[4], bp1s[4];
+  unsigned bp0s[4], bp1s[4], bp2s[4], bp3s[4];
   float bws[4][4];
   auto bcast = [&](int k) {
-    bis[k] = __shfl_sync(group_mask, i00, k, 4);
-    if constexpr (MATH == kFhfma) {
-      bp0s[k] = __shfl_sync(group_mask, pk0, k, 4);
-      bp1s[k] = __shfl_sync(group_mask, pk1, k, 4);
+    bis[k] = __shfl_sync(group_mask, i00, k, G);
+    if constexpr (kPackedW) {
+      bp0s[k] = __shfl_sync(group_mask, pk0, k, G);
+      bp1s[k] = __shfl_sync(group_mask, pk1, k, G);
+      if constexpr (MATH == kFhfmaSplit) {
+        bp2s[k] = __shfl_sync(group_mask, pk2, k, G);
+        bp3s[k] = __shfl_sync(group_mask, pk3, k, G);
+      }
     } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) bws[k][j] = __shfl_sync(group_mask, cw[j], k, 4);
+      for (int j = 0; j < 4; ++j) bws[k][j] = __shfl_sync(group_mask, cw[j], k, G);
     }
   };
 #pragma unroll
@@ -80,11 +92,15 @@ __device__ __forceinline__ void hp_level_samples(float (&acc)[8], int i00, unsig
     if (k + MSDA_HP_BCAST_AHEAD < 4) bcast(k + MSDA_HP_BCAST_AHEAD);
     uint4 rows[4];
     float bw[4];
-    unsigned bp0 = 0, bp1 = 0;
+    unsigned bp0 = 0, bp1 = 0, bp2 = 0, bp3 = 0;
     const int bi = bis[k];
-    if constexpr (MATH == kFhfma) {
+    if constexpr (kPackedW) {
       bp0 = bp0s[k];
       bp1 = bp1s[k];
+      if constexpr (MATH == kFhfmaSplit) {
+        bp2 = bp2s[k];
+        bp3 = bp3s[k];
+      }
     } else {
 #pragma unroll
       for (int j = 0; j < 4; ++j) bw[j] = bws[k][j];
@@ -92,7 +108,7 @@ __device__ __forceinline__ void hp_level_samples(float (&acc)[8], int i00, unsig
     bool on[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      if constexpr (MATH == kFhfma) on[j] = ((((j & 2) ? bp1 : bp0) >> ((j & 1) * 16)) & 0x7fffu) != 0u;
+      if constexpr (kPackedW) on[j] = ((((j & 2) ? bp1 : bp0) >> ((j & 1) * 16)) & 0x7fffu) != 0u;
       else on[j] = bw[j] != 0.f;
     }
     // two row addresses per sample (top-left, bottom-left); the right-hand corners are immediate offsets
@@ -107,11 +123,11 @@ __device__ __forceinline__ void hp_level_samples(float (&acc)[8], int i00, unsig
       rows[2] = make_uint4(bot.v[0], bot.v[1], bot.v[2], bot.v[3]);
       rows[3] = make_uint4(bot.v[4], bot.v[5], bot.v[6], bot.v[7]);
     } else if constexpr (SMEM) {
-      const unsigned s0 = sm_lane + (unsigned)bi * 128u, s1 = s0 + (unsigned)W * 128u;
+      const unsigned s0 = sm_lane + (unsigned)bi * SPIX, s1 = s0 + (unsigned)W * SPIX;
       if (on[0]) rows[0] = lds128(s0);
-      if (on[1]) rows[1] = lds128(s0 + 128u);
+      if (on[1]) rows[1] = lds128(s0 + SPIX);
       if (on[2]) rows[2] = lds128(s1);
-      if (on[3]) rows[3] = lds128(s1 + 128u);
+      if (on[3]) rows[3] = lds128(s1 + SPIX);
     } else {
       // signed: the top-left index is -1 (or -1 - W) when only right-hand / lower corners are inside the level
       const char *g0 = vm + (ptrdiff_t)bi * (ptrdiff_t)PIXB;
@@ -123,9 +139,13 @@ __device__ __forceinline__ void hp_level_samples(float (&acc)[8], int i00, unsig
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      if constexpr (MATH == kFhfma) {
+      if constexpr (kPackedW) {
         const unsigned w16 = (((j & 2) ? bp1 : bp0) >> ((j & 1) * 16)) & 0xffffu;
         if (on[j]) RowFma<T, kFhfma>::run(acc, rows[j], 0.f, w16);
+        if constexpr (MATH == kFhfmaSplit) {
+          const unsigned l16 = (((j & 2) ? bp3 : bp2) >> ((j & 1) * 16)) & 0xffffu;
+          if (on[j]) RowFma<T, kFhfma>::run(acc, rows[j], 0.f, l16);
+        }
       } else {
         if (on[j]) RowFma<T, kExact>::run(acc, rows[j], bw[j], 0u);
       }
@@ -163,8 +183,12 @@ __device__ __forceinline__ void make_geo_packed(float x, float y, float aw, int 
 // epilogue); `p.value` is not read.  No cached levels in that mode.
 template <typename T, int MATH, int MT, bool DYN = false, bool PACKED = false>
 __global__ void __launch_bounds__(kHpThreads, 1) msda_fwd_hp(const MsdaParams p) {
-  constexpr int D = 32, E = 2, VEC = 8;
-  extern __shared__ __align__(128) unsigned char hp_rows[];  // cached levels: [pixel][2 heads][64 B]
+  constexpr int D = 32, E = (int)sizeof(T), VEC = 16 / E;
+  constexpr int G = D * E / 16;       // lanes per (query, head) pair = 16-byte pieces of a corner row: 4 (16-bit), 8 (fp32)
+  constexpr int QPW = 32 / G / 2;     // queries per warp: 4 (16-bit), 2 (fp32)
+  constexpr int SPIX = 2 * D * E;     // bytes per pixel of a cached level (the head pair): 128 / 256
+  static_assert(!PACKED || E == 2, "the packed pyramid is a 16-bit layout");
+  extern __shared__ __align__(128) unsigned char hp_rows[];  // cached levels: [pixel][2 heads][D * E bytes]
   __shared__ HpLevel lv[kHpMaxLevels];
   __shared__ int s_first_cached;
 
@@ -198,9 +222,9 @@ __global__ void __launch_bounds__(kHpThreads, 1) msda_fwd_hp(const MsdaParams p)
     for (int l = p.L - 1; l >= 0; --l) {
       const long long n = (long long)lv[l].H * lv[l].W;
       const bool ok = !PACKED && lv[l].H > 0 && lv[l].W > 0 && lv[l].start >= 0 && (long long)lv[l].start + n <= (long long)p.S &&
-                      used + n * 128 <= (long long)p.hp_smem_bytes;
+                      used + n * SPIX <= (long long)p.hp_smem_bytes;
       if (!ok) break;
-      used += n * 128;
+      used += n * SPIX;
       l0 = l;
     }
     int off = 0;
@@ -213,30 +237,32 @@ __global__ void __launch_bounds__(kHpThreads, 1) msda_fwd_hp(const MsdaParams p)
   __syncthreads();
   const int l0 = s_first_cached;
 
-  // ---- copy the cached levels: 128 contiguous bytes (the head pair) per pixel ----
+  // ---- copy the cached levels: SPIX contiguous bytes (the head pair) per pixel ----
   for (int l = l0; l < p.L; ++l) {
-    const int n8 = lv[l].H * lv[l].W * 8;
-    const char *src = value + ((size_t)b * p.S + (size_t)lv[l].start) * pix_bytes + (size_t)hg * 128;
-    unsigned char *dst = hp_rows + (size_t)lv[l].base * 128;
+    constexpr int CH = SPIX / 16;
+    const int n8 = lv[l].H * lv[l].W * CH;
+    const char *src = value + ((size_t)b * p.S + (size_t)lv[l].start) * pix_bytes + (size_t)hg * SPIX;
+    unsigned char *dst = hp_rows + (size_t)lv[l].base * SPIX;
 #pragma unroll 4
     for (int i = threadIdx.x; i < n8; i += (int)blockDim.x) {
-      const int pix = i >> 3, c = i & 7;
-      *reinterpret_cast<uint4 *>(dst + (size_t)pix * 128 + c * 16) = ldg128(src + (size_t)pix * pix_bytes + c * 16);
+      const int pix = i / CH, c = i % CH;
+      *reinterpret_cast<uint4 *>(dst + (size_t)pix * SPIX + c * 16) = ldg128(src + (size_t)pix * pix_bytes + c * 16);
     }
   }
   __syncthreads();
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int grp = lane >> 2, sub = lane & 3;
-  const int qi = grp >> 1, hh = grp & 1;  // query of the warp's four, head of the pair
+  const int grp = lane / G, sub = lane % G;
+  const int qi = grp >> 1, hh = grp & 1;  // query of the warp's QPW, head of the pair
+  const int ks = sub & 3;                 // the sampling point this lane prepares (fp32: lanes 4..7 repeat 0..3)
   const int m = hg * 2 + hh;
   const int LP = p.L * 4;
-  const int units = (p.Q + 3) >> 2;
+  const int units = (p.Q + QPW - 1) / QPW;
   const int nw = (int)blockDim.x >> 5;  // warps per CTA: chosen by the host so that the units divide evenly
   const int stride = cpg * nw;
   constexpr int kHeadBytes = D * E * (PACKED ? 2 : 1), kLaneBytes = PACKED ? 32 : 16;
   const char *vm_img = value + (size_t)b * p.S * M * (size_t)kHeadBytes + (size_t)sub * kLaneBytes;  // head 0 of this image, this lane's bytes
-  const unsigned sm_lane = smem_u32(hp_rows) + (unsigned)(hh * 64 + sub * 16);
+  const unsigned sm_lane = smem_u32(hp_rows) + (unsigned)(hh * (D * E) + sub * 16);
 
   // Per-image bases are uniform; inside an image this lane's next sample is addressed by ONE running 32-bit byte
   // offset into the locations (its weight sits at half that offset: both arrays are [Q, M, L*4] with 4- and 2-byte
@@ -248,17 +274,25 @@ __global__ void __launch_bounds__(kHpThreads, 1) msda_fwd_hp(const MsdaParams p)
   auto unit_quad = [&](int idx) { return DYN ? idx / NG : idx; };
   auto unit_head = [&](int idx) { return (DYN ? idx % NG : hg) * 2 + hh; };
   const int total = DYN ? units * NG : units;
-  auto is_live = [&](int idx) { return idx < total && 4 * unit_quad(idx) + qi < p.Q; };
+  auto is_live = [&](int idx) { return idx < total && QPW * unit_quad(idx) + qi < p.Q; };
   // offset of point `sub` of level 0 of the pair that unit idx gives this lane group; padding slots (tail of the
   // last quad, units past the end) read pair 0 of the image and contribute / store nothing
   auto unit_offset = [&](int idx) -> unsigned {
-    return (is_live(idx) ? (unsigned)((4 * unit_quad(idx) + qi) * M + unit_head(idx)) * (unsigned)(LP * 2 * E) : 0u) + (unsigned)sub * 4u;
+    return (is_live(idx) ? (unsigned)((QPW * unit_quad(idx) + qi) * M + unit_head(idx)) * (unsigned)(LP * 2 * E) : 0u) + (unsigned)(ks * 2 * E);
   };
+  constexpr unsigned kLevelStep = 4u * 2u * (unsigned)E;  // bytes of locations per (pair, level): four points
   auto load_sample = [&](unsigned o) -> RawSample {
     RawSample r;
-    r.a = ld_stream_u32(loc_b + (size_t)o);
-    r.b = 0u;
-    r.w = (unsigned)ld_stream_u16(wgt_b + (size_t)(o >> 1));
+    if constexpr (E == 2) {
+      r.a = ld_stream_u32(loc_b + (size_t)o);
+      r.b = 0u;
+      r.w = (unsigned)ld_stream_u16(wgt_b + (size_t)(o >> 1));
+    } else {
+      const float2 xy = __ldg(reinterpret_cast<const float2 *>(loc_b + (size_t)o));
+      r.a = __float_as_uint(xy.x);
+      r.b = __float_as_uint(xy.y);
+      r.w = __float_as_uint(__ldg(reinterpret_cast<const float *>(wgt_b + (size_t)(o >> 1))));
+    }
     return r;
   };
 
@@ -269,7 +303,7 @@ __global__ void __launch_bounds__(kHpThreads, 1) msda_fwd_hp(const MsdaParams p)
   // loads therefore never sit between a warp and its next row loads.  Needs L >= 2 (host-checked).
   struct Geo {
     int i00, W;
-    unsigned pk0, pk1;
+    unsigned pk0, pk1, pk2, pk3;
     float cw[4];
   };
   auto geometry = [&](const RawSample &rw, int l, bool lv_live) -> Geo {
@@ -282,10 +316,15 @@ __global__ void __launch_bounds__(kHpThreads, 1) msda_fwd_hp(const MsdaParams p)
     if constexpr (PACKED) make_geo_packed(x, y, aw, H, g.W, g.i00, g.cw);
     else make_geo(x, y, aw, H, g.W, g.i00, g.cw);
     g.i00 += lv[l].base;
-    g.pk0 = g.pk1 = 0u;
-    if constexpr (MATH == kFhfma) {
+    g.pk0 = g.pk1 = g.pk2 = g.pk3 = 0u;
+    if constexpr (MATH == kFhfma || MATH == kFhfmaSplit) {
       g.pk0 = pack_weights<T>(g.cw[0], g.cw[1]);
       g.pk1 = pack_weights<T>(g.cw[2], g.cw[3]);
+    }
+    if constexpr (MATH == kFhfmaSplit) {  // residuals of the rounding above (exact in fp32: Sterbenz-like, same binade)
+      const float2 h0 = unpack2<T>(g.pk0), h1 = unpack2<T>(g.pk1);
+      g.pk2 = pack_weights<T>(g.cw[0] - h0.x, g.cw[1] - h0.y);
+      g.pk3 = pack_weights<T>(g.cw[2] - h1.x, g.cw[3] - h1.y);
     }
     return g;
   };
@@ -318,7 +357,7 @@ __global__ void __launch_bounds__(kHpThreads, 1) msda_fwd_hp(const MsdaParams p)
   unsigned off = unit_offset(cur);          // offset of the inputs held in `raw`
   bool live = is_live(cur);
   Geo geo = geometry(load_sample(off), 0, live);  // step 0
-  off += 16u;
+  off += kLevelStep;
   RawSample raw = load_sample(off);         // inputs of step 1 (level 1 of the first unit)
 
   int it = 0;
@@ -337,9 +376,9 @@ __global__ void __launch_bounds__(kHpThreads, 1) msda_fwd_hp(const MsdaParams p)
       // geometry of step t+1 from the inputs in `raw`; request the inputs of step t+2
       const bool wrap = l + 1 >= p.L;
       const Geo next = geometry(raw, wrap ? 0 : l + 1, wrap ? live_n : live);
-      off = (l + 2 == p.L) ? unit_offset(nxt) : off + 16u;
+      off = (l + 2 == p.L) ? unit_offset(nxt) : off + kLevelStep;
       raw = load_sample(off);
-      hp_level_samples<T, MATH, kSmem, MT * D * E * (PACKED ? 2 : 1), PACKED>(acc, geo.i00, geo.pk0, geo.pk1, geo.cw, geo.W, vm, sm_lane);
+      hp_level_samples<T, MATH, kSmem, MT * D * E * (PACKED ? 2 : 1), PACKED>(acc, geo.i00, geo.pk0, geo.pk1, geo.pk2, geo.pk3, geo.cw, geo.W, vm, sm_lane);
       geo = next;
     };
     // fine levels from global memory, then the cached coarse levels from shared memory
@@ -348,7 +387,7 @@ __global__ void __launch_bounds__(kHpThreads, 1) msda_fwd_hp(const MsdaParams p)
 #pragma unroll 1
     for (int l = l0; l < p.L; ++l) step(l, std::true_type{});
 
-    if (live) store_row<T, VEC>(out + ((size_t)b * p.Q * M + (size_t)(4 * unit_quad(cur) + qi) * M + unit_head(cur)) * D + sub * VEC, acc);
+    if (live) store_row<T, VEC>(out + ((size_t)b * p.Q * M + (size_t)(QPW * unit_quad(cur) + qi) * M + unit_head(cur)) * D + sub * VEC, acc);
     live = live_n;
     cur = nxt;
     nxt = after;

@@ -2321,20 +2321,24 @@ int forward_impl(MsdaParams p, int dtype, unsigned flags, void *workspace, size_
   }
 
   // ---- head-pair kernel: coarse levels in shared memory (msda_fwd_hp.cuh) ----
-  // 16-bit types, D = 32, P = 4, an even number of heads, and enough query quads to give every warp of every
-  // CTA work; MSDA_FLAG_NO_SMEM_LEVELS / MSDA_B200_HP=0 fall back to the all-global kernel below.
+  // fp16 / bf16 / fp32, D = 32, P = 4, eight heads, and enough query groups (4 queries per warp for the 16-bit types,
+  // 2 for fp32, whose corner rows are whole 128-byte lines read by 8 lanes) to give every warp of every CTA work;
+  // MSDA_FLAG_NO_SMEM_LEVELS / MSDA_B200_HP=0 fall back to the all-global kernel below.
   {
     const int NG = p.M / 2;
-    const bool hp_shape = E == 2 && p.D == 32 && p.P == 4 && p.M == 8 && p.L >= 2 && p.L <= kHpMaxLevels &&
+    const int qpw = E == 4 ? 2 : 4;
+    // bf16 without a math flag: FHFMA with each weight as two bf16 terms (msda_fwd_hp.cuh, kFhfmaSplit)
+    const bool hp_split = dtype == MSDA_BF16 && plan.math == kExact && !(flags & MSDA_FLAG_MATH_EXACT) && env_int("MSDA_B200_BF16_SPLIT", 1);
+    const bool hp_shape = (E == 2 || (E == 4 && env_int("MSDA_B200_HP_F32", 1))) && p.D == 32 && p.P == 4 && p.M == 8 && p.L >= 2 && p.L <= kHpMaxLevels &&
                           NG <= sms && !fused && plan.split == 1 && plan.stage_bytes == 0 && !plan.dyn &&
                           // exact-arithmetic calls (bf16 default, MSDA_FLAG_MATH_EXACT) stay on the vector kernel, which is
                           // 3 % faster for them at the headline shape (58.9 vs 60.6 us); MSDA_B200_HP_EXACT=1 overrides
-                          (plan.math == kFhfma || env_int("MSDA_B200_HP_EXACT", 0)) &&
-                          aligned_to(p.loc, 4) && !(flags & MSDA_FLAG_NO_SMEM_LEVELS) &&
+                          (plan.math == kFhfma || E == 4 || hp_split || env_int("MSDA_B200_HP_EXACT", 0)) &&
+                          aligned_to(p.loc, 2 * E) && aligned_to(p.weight, E) && !(flags & MSDA_FLAG_NO_SMEM_LEVELS) &&
                           // the kernel addresses an image's locations with 32-bit byte offsets
-                          (int64_t)p.Q * p.M * p.L * 16 < ((int64_t)1 << 32);
+                          (int64_t)p.Q * p.M * p.L * 8 * E < ((int64_t)1 << 32);
     const int cpg = NG > 0 ? sms / NG : 0;
-    const int64_t quads = ((int64_t)p.Q + 3) / 4;
+    const int64_t quads = ((int64_t)p.Q + qpw - 1) / qpw;
     const int64_t hp_min_quads = (int64_t)env_int("MSDA_B200_HP_MIN_QUADS_PER_WARP", 2) * cpg * (kHpThreads / 32);
     // Warps per CTA: every warp of the cpg CTAs of a head pair walks the query quads with the same stride, so the
     // call takes ceil(quads / (cpg * nw)) rounds; pick the nw (of the upper half of what the register budget
@@ -2377,16 +2381,20 @@ int forward_impl(MsdaParams p, int dtype, unsigned flags, void *workspace, size_
         if (hp_warps < 1 || hp_warps > kHpThreads / 32) hp_warps = kHpThreads / 32;
       }
       int rch;
-      if (dtype == MSDA_F16) {
+      if (dtype == MSDA_F32) {
+        rch = hp_dyn ? launch_hp(msda_fwd_hp<float, kExact, 8, true>) : launch_hp(msda_fwd_hp<float, kExact, 8>);
+      } else if (dtype == MSDA_F16) {
         if (hp_dyn) rch = plan.math == kFhfma ? launch_hp(msda_fwd_hp<__half, kFhfma, 8, true>) : launch_hp(msda_fwd_hp<__half, kExact, 8, true>);
         else rch = plan.math == kFhfma ? launch_hp(msda_fwd_hp<__half, kFhfma, 8>) : launch_hp(msda_fwd_hp<__half, kExact, 8>);
+      } else if (hp_split && !hp_dyn) {
+        rch = launch_hp(msda_fwd_hp<__nv_bfloat16, kFhfmaSplit, 8>);
       } else {
         if (hp_dyn) rch = plan.math == kFhfma ? launch_hp(msda_fwd_hp<__nv_bfloat16, kFhfma, 8, true>) : launch_hp(msda_fwd_hp<__nv_bfloat16, kExact, 8, true>);
         else rch = plan.math == kFhfma ? launch_hp(msda_fwd_hp<__nv_bfloat16, kFhfma, 8>) : launch_hp(msda_fwd_hp<__nv_bfloat16, kExact, 8>);
       }
       if (rch == 0)
         snprintf(g_last_variant, sizeof(g_last_variant), "hp<%s,D32,P4,M%d>/smem%dK/%dwarps/%s%s", dtype_name(dtype), p.M,
-                 p.hp_smem_bytes / 1024, hp_warps, plan.math == kFhfma ? "fhfma" : "exact", hp_dyn ? "/dyn" : "");
+                 p.hp_smem_bytes / 1024, hp_warps, plan.math == kFhfma ? "fhfma" : (hp_split && !hp_dyn) ? "fhfma-split" : "exact", hp_dyn ? "/dyn" : "");
       return rch;
     }
   }

@@ -20,8 +20,13 @@ from perf_sweep import KEYS, device_sets, time_calls
 
 WORKLOADS = {
     "headline": [("swinl_enc_1152x768", 1, "float16", None)],
+    "f32": [("swinl_enc_1152x768", 1, "float32", None), ("swinl_enc_1920x1280", 2, "float32", None),
+            ("r50_enc_608", 1, "float32", None), ("swinl_enc_1152x768", 1, "bfloat16", None)],
+    "bf16": [("swinl_enc_1152x768", 1, "bfloat16", None), ("r50_enc_608", 1, "bfloat16", None),
+             ("swinl_enc_1920x1280", 2, "bfloat16", None), ("swinl_enc_1152x768_s4", 1, "bfloat16", None)],
     "all": [("swinl_enc_1152x768", 1, "float16", None), ("swinl_enc_1152x768", 1, "float16", "uniform"),
             ("swinl_enc_1152x768", 4, "float16", None), ("swinl_enc_1152x768", 1, "bfloat16", None),
+            ("swinl_enc_1152x768", 1, "float32", None), ("swinl_enc_1920x1280", 2, "float32", None),
             ("r50_enc_608", 1, "float16", None), ("swinl_enc_1920x1280", 2, "float16", None),
             ("swinl_enc_1152x768_s4", 1, "float16", None), ("swinl_dec_1900q", 1, "float16", None)],
 }
@@ -31,7 +36,10 @@ def main():
     which = sys.argv[1] if len(sys.argv) > 1 else "headline"
     cfgs = [{"name": "vec (HP=0)", "MSDA_B200_HP": 0}]
     for kb in (os.environ.get("HP_SMEM_LIST", "148,200,100,64,0").split(",")):
-        cfgs.append({"name": f"hp smem{kb}K", "MSDA_B200_HP": 1, "MSDA_B200_HP_SMEM": int(kb) * 1024, "MSDA_B200_HP_MIN_QUADS_PER_WARP": 0})
+        cfgs.append({"name": f"hp smem{kb}K", "MSDA_B200_HP": 1, "MSDA_B200_HP_SMEM": int(kb) * 1024, "MSDA_B200_HP_MIN_QUADS_PER_WARP": 0,
+                     "MSDA_B200_HP_EXACT": int(os.environ.get("HP_EXACT", "0")), "MSDA_B200_BF16_SPLIT": 0})
+    if which == "bf16":
+        cfgs.append({"name": "hp split smem0K", "MSDA_B200_HP": 1, "MSDA_B200_HP_SMEM": 0, "MSDA_B200_HP_MIN_QUADS_PER_WARP": 0, "MSDA_B200_BF16_SPLIT": 1})
     dev = torch.device("cuda:0")
     rows = []
     for name, batch, dtn, loc_mode in WORKLOADS[which]:

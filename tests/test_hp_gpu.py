@@ -18,7 +18,7 @@ from parity import BF16_MAX_REL, HALF_MAX_REL, max_rel
 pytestmark = pytest.mark.gpu
 
 KEYS = ("value", "spatial_shapes", "level_start_index", "sampling_loc", "attn_weight")
-DT = {"f16": torch.float16, "bf16": torch.bfloat16}
+DT = {"f16": torch.float16, "bf16": torch.bfloat16, "f32": torch.float32}
 
 
 def _inputs(shapes, Q, B, seed, out_of_range=0.0, kind="encoder"):
@@ -51,7 +51,7 @@ SHAPES = [
 ]
 
 
-@pytest.mark.parametrize("dt", ["f16", "bf16"])
+@pytest.mark.parametrize("dt", ["f16", "bf16", "f32"])
 @pytest.mark.parametrize("smem_kb", [0, 8, 36, 148, 200])
 @pytest.mark.parametrize("shape_id", range(len(SHAPES)))
 def test_head_pair_kernel_is_bit_identical_to_vector_kernel(shape_id, smem_kb, dt, cuda_device, monkeypatch):
@@ -70,20 +70,31 @@ def test_head_pair_kernel_is_bit_identical_to_vector_kernel(shape_id, smem_kb, d
         got, v1 = _run(d, fl)
         assert cb.launch_count() == before + 1
         assert v1.startswith("hp<") and f"smem{smem_kb}K" in v1, v1
+        if dt == "bf16" and fl == 0:
+            # bf16 without a math flag: FHFMA with every weight as two bf16 terms (hi + lo, 2^-17 relative) -- not the
+            # vector kernel's fp32-weight arithmetic bit for bit, but inside one output rounding of it
+            assert v1.endswith("/fhfma-split"), v1
+            assert max_rel(got.float().cpu().numpy(), want.float().cpu().numpy()) <= BF16_MAX_REL
+            continue
         assert torch.equal(got, want), f"{v1} differs from {v0}: max abs {float((got.float() - want.float()).abs().max())}"
     # and against the C oracle (fp32 reference on the rounded inputs)
     ref = oracle.forward_c(d["value"].float().cpu().numpy(), inp.spatial_shapes, inp.level_start_index,
                            d["sampling_loc"].float().cpu().numpy(), d["attn_weight"].float().cpu().numpy())
     got, _ = _run(d, 0)
-    assert max_rel(got.float().cpu().numpy(), ref) <= (HALF_MAX_REL if dt == "f16" else BF16_MAX_REL)
+    if dt == "f32":  # fp32 (8 lanes per 128-byte corner row, 2 queries per warp): the fp32 gate, relative L2 <= 1e-5
+        g64 = got.cpu().numpy().astype(np.float64)
+        assert float(np.linalg.norm(g64 - ref) / np.linalg.norm(ref)) <= 1e-5
+    else:
+        assert max_rel(got.float().cpu().numpy(), ref) <= (HALF_MAX_REL if dt == "f16" else BF16_MAX_REL)
 
 
+@pytest.mark.parametrize("dt", ["f16", "f32"])
 @pytest.mark.parametrize("warps", [1, 7, 16, 25])
-def test_head_pair_kernel_any_warp_count(warps, cuda_device, monkeypatch):
+def test_head_pair_kernel_any_warp_count(warps, dt, cuda_device, monkeypatch):
     """The host picks the warps per CTA that balances the rounds; every count must give the same bits (including
     counts that leave whole warps without a unit)."""
     inp = _inputs(W.pyramid_shapes(256, 256), 0, 2, seed=5, out_of_range=0.1)
-    d = _dev(inp, torch.float16, cuda_device)
+    d = _dev(inp, DT[dt], cuda_device)
     monkeypatch.setenv("MSDA_B200_SPLIT", "1")
     monkeypatch.setenv("MSDA_B200_HP_MIN_QUADS_PER_WARP", "0")
     monkeypatch.setenv("MSDA_B200_HP_EXACT", "1")                   # also the exact-arithmetic instantiations (default: vector kernel)
@@ -122,7 +133,8 @@ def test_head_pair_kernel_output_fully_written_and_graph_safe(cuda_device, monke
     assert torch.equal(out2, want)
 
 
-def test_head_pair_kernel_non_finite_locations(cuda_device, monkeypatch):
+@pytest.mark.parametrize("dt", ["f16", "f32"])
+def test_head_pair_kernel_non_finite_locations(dt, cuda_device, monkeypatch):
     """NaN / infinite sampling locations fail the reference's range test (ms_deform_attn.cu:249): the sample
     contributes nothing and nothing is read for it."""
     monkeypatch.setenv("MSDA_B200_SPLIT", "1")
@@ -134,8 +146,8 @@ def test_head_pair_kernel_non_finite_locations(cuda_device, monkeypatch):
     rng = np.random.default_rng(3)
     bad = rng.random(loc.shape[:-1]) < 0.05
     loc[bad] = rng.choice(np.array([np.nan, np.inf, -np.inf, 1e30, -1e30], dtype=loc.dtype), size=(int(bad.sum()), 1))
-    d = _dev(inp, torch.float16, cuda_device)
-    d["sampling_loc"] = torch.from_numpy(loc).to(device=cuda_device, dtype=torch.float16)
+    d = _dev(inp, DT[dt], cuda_device)
+    d["sampling_loc"] = torch.from_numpy(loc).to(device=cuda_device, dtype=DT[dt])
     want, _ = _run(d, cb.FLAG_NO_SMEM_LEVELS)
     got, v = _run(d, 0)
     assert v.startswith("hp<")
@@ -182,3 +194,33 @@ def test_packed_value_pyramid_gather_is_bit_identical(dt, cuda_device, monkeypat
     with pytest.raises(RuntimeError):
         cb.forward_packed(packed, DT[dt], d["value"].shape[1], d["spatial_shapes"][:1].contiguous(), d["level_start_index"][:1].contiguous(),
                           d["sampling_loc"][:, :, :, :1].contiguous(), d["attn_weight"][:, :, :, :1].contiguous())
+
+
+def test_bf16_split_weight_fhfma_is_as_accurate_as_fp32_weights(cuda_device, monkeypatch):
+    """bf16's default on the head-pair kernel's shapes: each corner weight enters FHFMA as two bf16 terms (hi + lo).
+    Against the C oracle its worst error and its relative L2 must match the fp32-weight path's to within the split's
+    own 2^-17, and stay far from the single-bf16-weight FHFMA's (opt-in, 2^-9 per product)."""
+    monkeypatch.setenv("MSDA_B200_SPLIT", "1")
+    monkeypatch.setenv("MSDA_B200_HP_MIN_QUADS_PER_WARP", "0")
+    monkeypatch.setenv("MSDA_B200_HP_EXACT", "1")
+    inp = _inputs(W.pyramid_shapes(512, 384), 0, 1, seed=31, out_of_range=0.05)
+    d = _dev(inp, torch.bfloat16, cuda_device)
+    ref = oracle.forward_c(d["value"].float().cpu().numpy(), inp.spatial_shapes, inp.level_start_index,
+                           d["sampling_loc"].float().cpu().numpy(), d["attn_weight"].float().cpu().numpy())
+
+    def errs(flags):
+        out, v = _run(d, flags)
+        g = out.float().cpu().numpy().astype(np.float64)
+        return max_rel(g, ref), float(np.linalg.norm(g - ref) / np.linalg.norm(ref)), v
+
+    e_exact, l2_exact, v_exact = errs(cb.FLAG_MATH_EXACT)
+    e_split, l2_split, v_split = errs(0)
+    e_one, l2_one, v_one = errs(cb.FLAG_MATH_FHFMA)
+    assert v_exact.endswith("/exact") and v_split.endswith("/fhfma-split") and v_one.endswith("/fhfma"), (v_exact, v_split, v_one)
+    assert e_split <= BF16_MAX_REL and e_split <= e_exact + 2.0 ** -14
+    assert abs(l2_split - l2_exact) <= 1e-5
+    assert l2_one > l2_split * 1.15      # the single-term FHFMA is measurably worse: that is why it is not the default
+    # MSDA_B200_BF16_SPLIT=0 restores the fp32-weight default
+    monkeypatch.setenv("MSDA_B200_BF16_SPLIT", "0")
+    _, _, v = errs(0)
+    assert v.endswith("/exact"), v

@@ -399,7 +399,14 @@ def test_full_size_configs_against_oracle(name, dt, cuda_device):
     lin = cb.multi_scale_deformable_attention(*(d[k] for k in ARRAY_KEYS), flags=cb.FLAG_LINEAR_ORDER)
     assert torch.equal(out, lin)
     staged = cb.multi_scale_deformable_attention(*(d[k] for k in ARRAY_KEYS), flags=cb.FLAG_STAGE_TMA)
-    assert torch.equal(out, staged)
+    if dt == "bf16":
+        # bf16's default on the big shapes carries each weight as two bf16 terms (head-pair kernel, 2^-17 relative);
+        # the staged path uses fp32 weights: identical to MATH_EXACT, and within one output rounding of the default
+        exact = cb.multi_scale_deformable_attention(*(d[k] for k in ARRAY_KEYS), flags=cb.FLAG_MATH_EXACT)
+        assert torch.equal(exact, staged)
+        assert max_rel(out.float().cpu().numpy(), staged.float().cpu().numpy()) <= BF16_MAX_REL
+    else:
+        assert torch.equal(out, staged)
     if dt != "f32":
         # both 16-bit math modes meet the gate at full size
         for fl in (cb.FLAG_MATH_EXACT, cb.FLAG_MATH_FHFMA):
@@ -585,10 +592,13 @@ def test_dynamic_unit_scheduling_is_bit_identical(name, batch, dt, cuda_device, 
     stream capture must fall back to the strided schedule."""
     monkeypatch.setenv("MSDA_B200_SPLIT", "1")
     d = to_dev(_full_inputs(name, batch), TORCH_DT[dt], cuda_device)
-    want = cb.multi_scale_deformable_attention(*(d[k] for k in ARRAY_KEYS))
+    # bf16: pin the fp32-weight arithmetic (its default on this shape is the head-pair kernel's split-weight FHFMA,
+    # which the dynamically scheduled vector kernel does not implement)
+    fl = cb.FLAG_MATH_EXACT if dt == "bf16" else 0
+    want = cb.multi_scale_deformable_attention(*(d[k] for k in ARRAY_KEYS), flags=fl)
     assert not cb.last_variant().endswith("/dyn")
     monkeypatch.setenv("MSDA_B200_DYN", "1")
-    got = cb.multi_scale_deformable_attention(*(d[k] for k in ARRAY_KEYS))
+    got = cb.multi_scale_deformable_attention(*(d[k] for k in ARRAY_KEYS), flags=fl)
     assert cb.last_variant().endswith("/dyn")
     assert torch.equal(got, want)
     if name == "swinl_dec_1900q":

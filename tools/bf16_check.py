@@ -12,7 +12,8 @@ for name in ("swinl_enc_1152x768", "swinl_dec_1152x768", "swinl_enc_1920x1280"):
     d = {k: torch.from_numpy(getattr(inp, k)) for k in KEYS}
     d = {k: (v.to(dev) if v.dtype == torch.int64 else v.to(device=dev, dtype=torch.bfloat16)) for k, v in d.items()}
     ref = cb.multi_scale_deformable_attention(d["value"].float(), d["spatial_shapes"], d["level_start_index"], d["sampling_loc"].float(), d["attn_weight"].float()).cpu().numpy()
-    for fl, nm in ((cb.FLAG_MATH_EXACT, "exact"), (cb.FLAG_MATH_FHFMA, "fhfma")):
+    for fl, nm in ((cb.FLAG_MATH_EXACT, "exact"), (cb.FLAG_MATH_FHFMA, "fhfma"), (0, "default"), (0, "split")):
+        os.environ["MSDA_B200_BF16_SPLIT"] = "1" if nm == "split" else "0"
         out = cb.multi_scale_deformable_attention(*(d[k] for k in KEYS), flags=fl).float().cpu().numpy()
         calls = [cb.PreparedForward(*(d[k] for k in KEYS), flags=fl)]
         for _ in range(20): calls[0]()
@@ -21,4 +22,4 @@ for name in ("swinl_enc_1152x768", "swinl_dec_1152x768", "swinl_enc_1920x1280"):
         s.record()
         for _ in range(200): calls[0]()
         e.record(); torch.cuda.synchronize()
-        print(name, nm, "max_rel %.3e" % max_rel(out, ref), "ulp %.3f" % bf16_ulp_errors(out, ref), "rel_l2 %.3e" % (np.linalg.norm(out-ref)/np.linalg.norm(ref)), "%.2f us (L2-warm)" % (1e3*s.elapsed_time(e)/200))
+        print(name, nm, "max_rel %.3e" % max_rel(out, ref), "ulp %.3f" % bf16_ulp_errors(out, ref), "rel_l2 %.3e" % (np.linalg.norm(out-ref)/np.linalg.norm(ref)), "%.2f us (L2-warm)" % (1e3*s.elapsed_time(e)/200), cb.last_variant())
