@@ -39,6 +39,13 @@ struct HpLevel {
   int start;  // first key of the level in the value tensor
 };
 
+// one 32-byte load straight into two row registers (packed pyramid: a pixel's row and its right-hand neighbour's)
+__device__ __forceinline__ void ldg256_pair(uint4 &a, uint4 &b, const void *ptr) {
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+               : "l"(ptr));
+}
+
 __device__ __forceinline__ uint4 lds128(unsigned addr) {
   uint4 r;
   asm("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
@@ -62,94 +69,115 @@ __device__ __forceinline__ void hp_level_samples(float (&acc)[16 / sizeof(T)], i
   constexpr unsigned group_mask = 0xffffffffu;
   constexpr int G = 32 * (int)sizeof(T) / 16;   // lanes per corner row: 4 (16-bit), 8 (fp32: a row is a whole 128-byte line)
   constexpr unsigned SPIX = 64u * (unsigned)sizeof(T);  // bytes per pixel of a cached level: two heads x 32 channels
-  // The broadcasts of sample k + MSDA_HP_BCAST_AHEAD can be written ahead of sample k's loads (the ncu source view
-  // shows 14 % of the stall samples on the predicate tests waiting for their shuffle).  Measured at the headline shape:
-  // 0 / 1 / 2 / 4 samples ahead = 44.59 / 44.59 / 44.91 / 44.96 us -- ptxas schedules the shuffles itself; default 0.
-#ifndef MSDA_HP_BCAST_AHEAD
-#define MSDA_HP_BCAST_AHEAD 0
+  // Row loads are written MSDA_HP_DEPTH samples (x 4 corner rows) ahead of the FMAs that consume them.  ptxas keeps the
+  // order it is given as far as registers allow: depth 1 leaves 4 row loads in flight per lane whatever the register
+  // budget; depth 2 / 4 hold 8 / 16 (32 / 64 registers of rows) and need the smaller CTAs of MSDA_HP_THREADS.
+#ifndef MSDA_HP_DEPTH
+#define MSDA_HP_DEPTH 1
 #endif
-  int bis[4];
-  unsigned bp0s[4], bp1s[4], bp2s[4], bp3s[4];
-  float bws[4][4];
-  auto bcast = [&](int k) {
-    bis[k] = __shfl_sync(group_mask, i00, k, G);
-    if constexpr (kPackedW) {
-      bp0s[k] = __shfl_sync(group_mask, pk0, k, G);
-      bp1s[k] = __shfl_sync(group_mask, pk1, k, G);
-      if constexpr (MATH == kFhfmaSplit) {
-        bp2s[k] = __shfl_sync(group_mask, pk2, k, G);
-        bp3s[k] = __shfl_sync(group_mask, pk3, k, G);
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) bws[k][j] = __shfl_sync(group_mask, cw[j], k, G);
-    }
+  struct Slot {
+    uint4 r0, r1, r2, r3;
+    unsigned p0, p1, p2, p3;
+    float w0, w1, w2, w3;
+    bool o0, o1, o2, o3;  // corner inside the level and weighted: its row is loaded and accumulated
   };
-#pragma unroll
-  for (int k = 0; k < MSDA_HP_BCAST_AHEAD && k < 4; ++k) bcast(k);
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    if (k + MSDA_HP_BCAST_AHEAD < 4) bcast(k + MSDA_HP_BCAST_AHEAD);
-    uint4 rows[4];
-    float bw[4];
-    unsigned bp0 = 0, bp1 = 0, bp2 = 0, bp3 = 0;
-    const int bi = bis[k];
+  auto corner_on = [](const Slot &s, int j) -> bool {
+    if constexpr (kPackedW) return ((((j & 2) ? s.p1 : s.p0) >> ((j & 1) * 16)) & 0x7fffu) != 0u;
+    else return (j == 0 ? s.w0 : j == 1 ? s.w1 : j == 2 ? s.w2 : s.w3) != 0.f;
+  };
+  auto issue = [&](Slot &s, int k) {
+    const int bi = __shfl_sync(group_mask, i00, k, G);
+    s.p0 = s.p1 = s.p2 = s.p3 = 0u;
+    s.w0 = s.w1 = s.w2 = s.w3 = 0.f;
     if constexpr (kPackedW) {
-      bp0 = bp0s[k];
-      bp1 = bp1s[k];
+      s.p0 = __shfl_sync(group_mask, pk0, k, G);
+      s.p1 = __shfl_sync(group_mask, pk1, k, G);
       if constexpr (MATH == kFhfmaSplit) {
-        bp2 = bp2s[k];
-        bp3 = bp3s[k];
+        s.p2 = __shfl_sync(group_mask, pk2, k, G);
+        s.p3 = __shfl_sync(group_mask, pk3, k, G);
       }
     } else {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) bw[j] = bws[k][j];
+      s.w0 = __shfl_sync(group_mask, cw[0], k, G);
+      s.w1 = __shfl_sync(group_mask, cw[1], k, G);
+      s.w2 = __shfl_sync(group_mask, cw[2], k, G);
+      s.w3 = __shfl_sync(group_mask, cw[3], k, G);
     }
-    bool on[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if constexpr (kPackedW) on[j] = ((((j & 2) ? bp1 : bp0) >> ((j & 1) * 16)) & 0x7fffu) != 0u;
-      else on[j] = bw[j] != 0.f;
-    }
+    s.o0 = corner_on(s, 0);
+    s.o1 = corner_on(s, 1);
+    s.o2 = corner_on(s, 2);
+    s.o3 = corner_on(s, 3);
+    const bool o0 = s.o0, o1 = s.o1, o2 = s.o2, o3 = s.o3;
     // two row addresses per sample (top-left, bottom-left); the right-hand corners are immediate offsets
     if constexpr (PACKED) {
       const char *g0 = vm + (ptrdiff_t)bi * (ptrdiff_t)PIXB;
       const char *g1 = vm + (ptrdiff_t)(bi + W) * (ptrdiff_t)PIXB;
-      U8 top, bot;
-      if (on[0] || on[1]) top = ldg256(g0);
-      if (on[2] || on[3]) bot = ldg256(g1);
-      rows[0] = make_uint4(top.v[0], top.v[1], top.v[2], top.v[3]);
-      rows[1] = make_uint4(top.v[4], top.v[5], top.v[6], top.v[7]);
-      rows[2] = make_uint4(bot.v[0], bot.v[1], bot.v[2], bot.v[3]);
-      rows[3] = make_uint4(bot.v[4], bot.v[5], bot.v[6], bot.v[7]);
+      if (o0 || o1) ldg256_pair(s.r0, s.r1, g0);
+      if (o2 || o3) ldg256_pair(s.r2, s.r3, g1);
     } else if constexpr (SMEM) {
       const unsigned s0 = sm_lane + (unsigned)bi * SPIX, s1 = s0 + (unsigned)W * SPIX;
-      if (on[0]) rows[0] = lds128(s0);
-      if (on[1]) rows[1] = lds128(s0 + SPIX);
-      if (on[2]) rows[2] = lds128(s1);
-      if (on[3]) rows[3] = lds128(s1 + SPIX);
+      if (o0) s.r0 = lds128(s0);
+      if (o1) s.r1 = lds128(s0 + SPIX);
+      if (o2) s.r2 = lds128(s1);
+      if (o3) s.r3 = lds128(s1 + SPIX);
     } else {
       // signed: the top-left index is -1 (or -1 - W) when only right-hand / lower corners are inside the level
       const char *g0 = vm + (ptrdiff_t)bi * (ptrdiff_t)PIXB;
       const char *g1 = vm + (ptrdiff_t)(bi + W) * (ptrdiff_t)PIXB;
-      if (on[0]) rows[0] = ldg128(g0);
-      if (on[1]) rows[1] = ldg128(g0 + PIXB);
-      if (on[2]) rows[2] = ldg128(g1);
-      if (on[3]) rows[3] = ldg128(g1 + PIXB);
+      if (o0) s.r0 = ldg128(g0);
+      if (o1) s.r1 = ldg128(g0 + PIXB);
+      if (o2) s.r2 = ldg128(g1);
+      if (o3) s.r3 = ldg128(g1 + PIXB);
     }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if constexpr (kPackedW) {
-        const unsigned w16 = (((j & 2) ? bp1 : bp0) >> ((j & 1) * 16)) & 0xffffu;
-        if (on[j]) RowFma<T, kFhfma>::run(acc, rows[j], 0.f, w16);
-        if constexpr (MATH == kFhfmaSplit) {
-          const unsigned l16 = (((j & 2) ? bp3 : bp2) >> ((j & 1) * 16)) & 0xffffu;
-          if (on[j]) RowFma<T, kFhfma>::run(acc, rows[j], 0.f, l16);
-        }
-      } else {
-        if (on[j]) RowFma<T, kExact>::run(acc, rows[j], bw[j], 0u);
+  };
+  auto corner = [&](const Slot &s, int j, bool on, const uint4 &row, float w) {
+    if constexpr (kPackedW) {
+      const unsigned w16 = (((j & 2) ? s.p1 : s.p0) >> ((j & 1) * 16)) & 0xffffu;
+      if (on) RowFma<T, kFhfma>::run(acc, row, 0.f, w16);
+      if constexpr (MATH == kFhfmaSplit) {
+        // keep the two 8-FMA groups apart: merged into one 16-instruction conditional block they are compiled as a
+        // branch instead of predicated FMAs (57.4 instead of 50.6 us at the headline shape)
+        asm volatile("");
+        const unsigned l16 = (((j & 2) ? s.p3 : s.p2) >> ((j & 1) * 16)) & 0xffffu;
+        if (on) RowFma<T, kFhfma>::run(acc, row, 0.f, l16);
       }
+    } else {
+      if (on) RowFma<T, kExact>::run(acc, row, w, 0u);
     }
+  };
+  auto consume = [&](const Slot &s) {
+    corner(s, 0, s.o0, s.r0, s.w0);
+    corner(s, 1, s.o1, s.r1, s.w1);
+    corner(s, 2, s.o2, s.r2, s.w2);
+    corner(s, 3, s.o3, s.r3, s.w3);
+  };
+  constexpr int DEPTH = (SMEM || PACKED) ? 1 : MSDA_HP_DEPTH;
+  static_assert(DEPTH == 1 || DEPTH == 2 || DEPTH == 4, "MSDA_HP_DEPTH: 1, 2 or 4 samples of row loads ahead");
+  if constexpr (DEPTH == 1) {
+    Slot a;
+    issue(a, 0); consume(a);
+    issue(a, 1); consume(a);
+    issue(a, 2); consume(a);
+    issue(a, 3); consume(a);
+  } else if constexpr (DEPTH == 2) {
+    Slot a, b;
+    issue(a, 0);
+    issue(b, 1);
+    consume(a);
+    issue(a, 2);
+    consume(b);
+    issue(b, 3);
+    consume(a);
+    consume(b);
+  } else {
+    Slot a, b, c, d;
+    issue(a, 0);
+    issue(b, 1);
+    issue(c, 2);
+    issue(d, 3);
+    consume(a);
+    consume(b);
+    consume(c);
+    consume(d);
   }
 }
 

@@ -12,8 +12,10 @@ for name in ("swinl_enc_1152x768", "swinl_dec_1152x768", "swinl_enc_1920x1280"):
     d = {k: torch.from_numpy(getattr(inp, k)) for k in KEYS}
     d = {k: (v.to(dev) if v.dtype == torch.int64 else v.to(device=dev, dtype=torch.bfloat16)) for k, v in d.items()}
     ref = cb.multi_scale_deformable_attention(d["value"].float(), d["spatial_shapes"], d["level_start_index"], d["sampling_loc"].float(), d["attn_weight"].float()).cpu().numpy()
-    for fl, nm in ((cb.FLAG_MATH_EXACT, "exact"), (cb.FLAG_MATH_FHFMA, "fhfma"), (0, "default"), (0, "split")):
-        os.environ["MSDA_B200_BF16_SPLIT"] = "1" if nm == "split" else "0"
+    for fl, nm in ((cb.FLAG_MATH_EXACT, "exact"), (cb.FLAG_MATH_FHFMA, "fhfma"), (0, "default"), (0, "nosplit")):
+        os.environ.pop("MSDA_B200_BF16_SPLIT", None)
+        if nm == "nosplit":
+            os.environ["MSDA_B200_BF16_SPLIT"] = "0"
         out = cb.multi_scale_deformable_attention(*(d[k] for k in KEYS), flags=fl).float().cpu().numpy()
         calls = [cb.PreparedForward(*(d[k] for k in KEYS), flags=fl)]
         for _ in range(20): calls[0]()

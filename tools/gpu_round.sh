@@ -6,6 +6,7 @@
 #   bench      bench.py (N=1) + reference arm     scaleN    bench.py under torchrun with N = $GPUS ranks (gpurun --gpus N)
 #   ncu        launch list of the bench command + `--set full` capture of the headline kernel (+ profiles/traffic.json)
 #   ncudec     `--set full` capture of the decoder call       ncuvec   same for the all-global vector kernel (MSDA_B200_HP=0)
+#   ncudtypes  `--set full` captures of the headline shape in bf16 and fp32      hpdtypes   their A/B timings + bf16 accuracy
 #   hp         head-pair kernel A/B against the vector kernel on every workload (tests/perf_hp.py)
 #   hpsweep    warps-per-CTA / shared-memory sweep of the head-pair kernel, both register builds
 #   sweep      tests/perf_sweep.py (all configurations, reference CUDA kernel beside ours)
@@ -47,6 +48,13 @@ for st in $STAGES; do
       python tools/update_traffic.py gpurun_out/prof_decoder.ncu-rep swinl_dec_1152x768/float16/b1 0 "profiles/r02_ncu_decoder_summary.txt (gpurun_out/prof_decoder.ncu-rep)" ;;
     ncuvec)
       NCU_ARGS="swinl_enc_1152x768 float16 1" ncu_full vec MSDA_B200_HP=0 ;;
+    ncudtypes)
+      NCU_ARGS="swinl_enc_1152x768 bfloat16 1" ncu_full bf16 MSDA_B200_HP=1
+      NCU_ARGS="swinl_enc_1152x768 float32 1" ncu_full f32 MSDA_B200_HP=1 ;;
+    hpdtypes)
+      HP_EXACT=1 HP_TAG=_f32 HP_SMEM_LIST=148,0 timeout 300 python tests/perf_hp.py f32 2>&1 | tee gpurun_out/perf_hp_f32.log | tail -14
+      HP_EXACT=1 HP_TAG=_bf16 HP_SMEM_LIST=0 timeout 300 python tests/perf_hp.py bf16 2>&1 | tee gpurun_out/perf_hp_bf16.log | tail -14
+      python tools/bf16_check.py 2>&1 | tee gpurun_out/bf16_check.log | tail -14 ;;
     hp)
       HP_SMEM_LIST=${SMEMS:-148,0} timeout 900 python tests/perf_hp.py all 2>&1 | tee gpurun_out/perf_hp_all.log | tail -30 ;;
     hpsweep)
