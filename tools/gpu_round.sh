@@ -8,7 +8,7 @@
 #   ncudec     `--set full` capture of the decoder call       ncuvec   same for the all-global vector kernel (MSDA_B200_HP=0)
 #   ncudtypes  `--set full` captures of the headline shape in bf16 and fp32      hpdtypes   their A/B timings + bf16 accuracy
 #   hp         head-pair kernel A/B against the vector kernel on every workload (tests/perf_hp.py)
-#   hpsweep    warps-per-CTA / shared-memory sweep of the head-pair kernel, both register builds
+#   hpsweep    warps-per-CTA / shared-memory sweep of the head-pair kernel + every tuning build under build_variants/
 #   sweep      tests/perf_sweep.py (all configurations, reference CUDA kernel beside ours)
 #   probe      tools/gather_probe.cu row-gather ceilings (+ ncu wavefront accounting)
 #   api        host cost per binding: C ABI / plugin entry / torch op on three workloads
@@ -61,8 +61,11 @@ for st in $STAGES; do
       for w in 25 24 21 16; do
         echo "== default build (<= 800 threads), warps=$w"; MSDA_B200_HP_WARPS=$w HP_TAG=_w$w HP_SMEM_LIST=${SMEMS:-148,0} python tests/perf_hp.py headline 2>&1 | grep "hp smem"
       done
-      for w in 32 29 25; do
-        echo "== 1024-thread build, warps=$w"; MSDA_B200_LIB=$PWD/build_variants/libmsda_hp1024.so MSDA_B200_HP_WARPS=$w HP_TAG=_1024_w$w HP_SMEM_LIST=${SMEMS:-148,0} python tests/perf_hp.py headline 2>&1 | grep "hp smem"
+      # tuning builds (python tools/build_variant.py NAME -DMSDA_HP_THREADS=.. -DMSDA_HP_DEPTH=..): every libmsda_*.so found
+      for lib in build_variants/libmsda_*.so; do
+        [ -f "$lib" ] || continue
+        v=$(basename $lib .so); echo "== $v"
+        MSDA_B200_LIB=$PWD/$lib HP_TAG=_$v HP_SMEM_LIST=${SMEMS:-0} python tests/perf_hp.py ${HP_SET:-headline} 2>&1 | grep "hp smem\|hp split"
       done ;;
     sweep)
       timeout 1200 python tests/perf_sweep.py --out gpurun_out/sweep.json > gpurun_out/sweep.log 2>&1; echo "sweep exit $?"; tail -3 gpurun_out/sweep.log ;;
