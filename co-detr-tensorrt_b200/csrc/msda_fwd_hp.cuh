@@ -38,6 +38,12 @@ struct HpLevel {
   int base;   // first key of the level in the value tensor, or (cached level) its first 128-byte entry in shared memory
   int start;  // first key of the level in the value tensor
 };
+// threads per CTA of the fused-producer instantiations: softmax statistics of two units, the reference point of the
+// step in flight and a second running offset need ~10 more registers than the plain kernel's 72
+#ifndef MSDA_HP_FUSED_THREADS
+#define MSDA_HP_FUSED_THREADS 800
+#endif
+constexpr int kHpFusedThreads = MSDA_HP_FUSED_THREADS;
 
 // one 32-byte load straight into two row registers (packed pyramid: a pixel's row and its right-hand neighbour's)
 __device__ __forceinline__ void ldg256_pair(uint4 &a, uint4 &b, const void *ptr) {
@@ -209,16 +215,22 @@ __device__ __forceinline__ void make_geo_packed(float x, float y, float aw, int 
 // head pair's quads (no cached levels in that mode: a CTA is no longer tied to one head pair).
 // PACKED: `p.packed` holds the pixel-pair packed pyramid (written by msda_pack_value or by the projection kernel's
 // epilogue); `p.value` is not read.  No cached levels in that mode.
-template <typename T, int MATH, int MT, bool DYN = false, bool PACKED = false>
-__global__ void __launch_bounds__(kHpThreads, 1) msda_fwd_hp(const MsdaParams p) {
+// FUSED: `p.offsets` / `p.logits` / `p.ref` in place of locations and weights (msda_b200_forward_fused): the softmax over
+// a pair's L*4 logits and the location arithmetic of multi_scale_deformable_attention.py:180-200 run in the geometry
+// lanes, rounding where the unfused pipeline rounds -- the same helpers, in the same order, as the vector kernel's
+// fused mode, so the two are bit-identical.
+template <typename T, int MATH, int MT, bool DYN = false, bool PACKED = false, bool FUSED = false>
+__global__ void __launch_bounds__(FUSED ? kHpFusedThreads : kHpThreads, 1) msda_fwd_hp(const MsdaParams p) {
   constexpr int D = 32, E = (int)sizeof(T), VEC = 16 / E;
   constexpr int G = D * E / 16;       // lanes per (query, head) pair = 16-byte pieces of a corner row: 4 (16-bit), 8 (fp32)
   constexpr int QPW = 32 / G / 2;     // queries per warp: 4 (16-bit), 2 (fp32)
   constexpr int SPIX = 2 * D * E;     // bytes per pixel of a cached level (the head pair): 128 / 256
   static_assert(!PACKED || E == 2, "the packed pyramid is a 16-bit layout");
+  static_assert(!FUSED || (!DYN && !PACKED), "fused producers: static schedule, plain value tensor");
   extern __shared__ __align__(128) unsigned char hp_rows[];  // cached levels: [pixel][2 heads][D * E bytes]
   __shared__ HpLevel lv[kHpMaxLevels];
   __shared__ int s_first_cached;
+  __shared__ float2 lv_rcp[FUSED ? kHpMaxLevels : 1];  // correctly rounded (1 / W, 1 / H): the fused producers' offset normalisation
 
   pdl_launch_dependents();
   pdl_wait_prior_grid();
@@ -231,8 +243,8 @@ __global__ void __launch_bounds__(kHpThreads, 1) msda_fwd_hp(const MsdaParams p)
   const int b = blockIdx.y;
   const unsigned pix_bytes = (unsigned)(M * D * E) * (PACKED ? 2u : 1u);  // packed entries are 128 bytes per head
   const char *__restrict__ value = static_cast<const char *>(PACKED ? p.packed : p.value);
-  const T *__restrict__ loc = static_cast<const T *>(p.loc);
-  const T *__restrict__ wgt = static_cast<const T *>(p.weight);
+  const T *__restrict__ loc = static_cast<const T *>(FUSED ? p.offsets : p.loc);
+  const T *__restrict__ wgt = static_cast<const T *>(FUSED ? p.logits : p.weight);
   T *__restrict__ out = static_cast<T *>(p.out);
 
   // ---- level table; which levels fit into the shared memory this launch was given ----
@@ -242,6 +254,9 @@ __global__ void __launch_bounds__(kHpThreads, 1) msda_fwd_hp(const MsdaParams p)
     lv[l].W = (int)__ldg(p.shapes + 2 * l + 1);
     lv[l].start = (int)__ldg(p.starts + l);
     lv[l].base = lv[l].start;
+    if constexpr (FUSED) {
+      lv_rcp[l] = make_float2(__frcp_rn((float)(lv[l].W > 0 ? lv[l].W : 1)), __frcp_rn((float)(lv[l].H > 0 ? lv[l].H : 1)));
+    }
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -309,6 +324,57 @@ __global__ void __launch_bounds__(kHpThreads, 1) msda_fwd_hp(const MsdaParams p)
     return (is_live(idx) ? (unsigned)((QPW * unit_quad(idx) + qi) * M + unit_head(idx)) * (unsigned)(LP * 2 * E) : 0u) + (unsigned)(ks * 2 * E);
   };
   constexpr unsigned kLevelStep = 4u * 2u * (unsigned)E;  // bytes of locations per (pair, level): four points
+  // fused producers: the query's reference point of the step's level travels with the step's inputs (one 32-bit
+  // running offset of its own: `ref` is [Q, L, ref_dim]), the softmax statistics of a pair are worked out one unit ahead
+  struct RefRaw {
+    unsigned r[4];  // 16-bit: r[0] = (x, y), r[1] = (w, h); fp32: x, y, w, h
+  };
+  struct Stats {
+    float mx, inv;
+  };
+  const char *ref_b = FUSED ? static_cast<const char *>(p.ref) + (size_t)b * p.Q * p.L * p.ref_dim * E : nullptr;
+  const unsigned ref_step = FUSED ? (unsigned)(p.ref_dim * E) : 0u;
+  auto ref_offset = [&](int idx) -> unsigned {
+    return is_live(idx) ? (unsigned)((QPW * unit_quad(idx) + qi) * p.L) * ref_step : 0u;
+  };
+  auto load_ref = [&](unsigned o) -> RefRaw {
+    RefRaw r;
+    r.r[0] = r.r[1] = r.r[2] = r.r[3] = 0u;
+    if constexpr (FUSED) {
+      const unsigned *q = reinterpret_cast<const unsigned *>(ref_b + (size_t)o);
+      if constexpr (E == 2) {
+        r.r[0] = __ldg(q);
+        if (p.ref_dim == 4) r.r[1] = __ldg(q + 1);
+      } else {
+        r.r[0] = __ldg(q);
+        r.r[1] = __ldg(q + 1);
+        if (p.ref_dim == 4) {
+          r.r[2] = __ldg(q + 2);
+          r.r[3] = __ldg(q + 3);
+        }
+      }
+    }
+    return r;
+  };
+  // maximum and 1 / sum of exp over the pair's L*4 logits: lane ks holds point ks of every level, the four point
+  // lanes complete both with two butterflies (same order as the vector kernel's fused mode)
+  auto softmax_stats = [&](int idx) -> Stats {
+    Stats st{0.f, 1.f};
+    if constexpr (FUSED) {
+      const T *lg = reinterpret_cast<const T *>(wgt_b + (size_t)(unit_offset(idx) >> 1));
+      float mx = -INFINITY;
+      for (int l = 0; l < p.L; ++l) mx = fmaxf(mx, Elem<T>::to_acc(lg[l * 4]));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      float sum = 0.f;
+      for (int l = 0; l < p.L; ++l) sum += fused_exp<T>(Elem<T>::to_acc(lg[l * 4]) - mx);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+      st.mx = mx;
+      st.inv = 1.f / sum;
+    }
+    return st;
+  };
   auto load_sample = [&](unsigned o) -> RawSample {
     RawSample r;
     if constexpr (E == 2) {
@@ -334,12 +400,28 @@ __global__ void __launch_bounds__(kHpThreads, 1) msda_fwd_hp(const MsdaParams p)
     unsigned pk0, pk1, pk2, pk3;
     float cw[4];
   };
-  auto geometry = [&](const RawSample &rw, int l, bool lv_live) -> Geo {
+  auto geometry = [&](const RawSample &rw, const RefRaw &rr, const Stats &st, int l, bool lv_live) -> Geo {
     Geo g;
     const int H = lv[l].H;
     g.W = lv[l].W;
     float x, y, aw;
     decode_raw<T>(rw, x, y, aw);
+    if constexpr (FUSED) {
+      // x, y are the raw offsets, aw the logit
+      T rf[4];
+      if constexpr (E == 2) {
+        const unsigned short h[4] = {(unsigned short)(rr.r[0] & 0xffffu), (unsigned short)(rr.r[0] >> 16), (unsigned short)(rr.r[1] & 0xffffu),
+                                     (unsigned short)(rr.r[1] >> 16)};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) rf[i] = *reinterpret_cast<const T *>(&h[i]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) rf[i] = __uint_as_float(rr.r[i]);
+      }
+      const float ox = x, oy = y;
+      fused_location_fast<T>(rf, p.ref_dim, ox, oy, (float)g.W, (float)H, lv_rcp[l].x, lv_rcp[l].y, x, y);
+      aw = round_like<T, float>(fused_exp<T>(aw - st.mx) * st.inv);
+    }
     aw = lv_live ? aw : 0.f;
     if constexpr (PACKED) make_geo_packed(x, y, aw, H, g.W, g.i00, g.cw);
     else make_geo(x, y, aw, H, g.W, g.i00, g.cw);
@@ -383,10 +465,14 @@ __global__ void __launch_bounds__(kHpThreads, 1) msda_fwd_hp(const MsdaParams p)
   asm volatile("" : "+l"(vm));  // one opaque 64-bit base: every corner address is a single IMAD.WIDE
 
   unsigned off = unit_offset(cur);          // offset of the inputs held in `raw`
+  unsigned roff = ref_offset(cur);
   bool live = is_live(cur);
-  Geo geo = geometry(load_sample(off), 0, live);  // step 0
+  Stats st_c = softmax_stats(cur);
+  Geo geo = geometry(load_sample(off), load_ref(roff), st_c, 0, live);  // step 0
   off += kLevelStep;
+  roff += ref_step;
   RawSample raw = load_sample(off);         // inputs of step 1 (level 1 of the first unit)
+  RefRaw rraw = load_ref(roff);
 
   int it = 0;
 #pragma unroll 1
@@ -395,6 +481,7 @@ __global__ void __launch_bounds__(kHpThreads, 1) msda_fwd_hp(const MsdaParams p)
     if constexpr (DYN) after = draw();      // the unit after next: the atomic's latency hides behind this unit
     else after = nxt + stride;
     const bool live_n = is_live(nxt);
+    const Stats st_n = softmax_stats(nxt);  // used by the last step of this unit (geometry of the next unit's level 0)
     float acc[VEC];
 #pragma unroll
     for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
@@ -403,9 +490,13 @@ __global__ void __launch_bounds__(kHpThreads, 1) msda_fwd_hp(const MsdaParams p)
       constexpr bool kSmem = decltype(smem_tag)::value;
       // geometry of step t+1 from the inputs in `raw`; request the inputs of step t+2
       const bool wrap = l + 1 >= p.L;
-      const Geo next = geometry(raw, wrap ? 0 : l + 1, wrap ? live_n : live);
+      const Geo next = geometry(raw, rraw, wrap ? st_n : st_c, wrap ? 0 : l + 1, wrap ? live_n : live);
       off = (l + 2 == p.L) ? unit_offset(nxt) : off + kLevelStep;
       raw = load_sample(off);
+      if constexpr (FUSED) {
+        roff = (l + 2 == p.L) ? ref_offset(nxt) : roff + ref_step;
+        rraw = load_ref(roff);
+      }
       hp_level_samples<T, MATH, kSmem, MT * D * E * (PACKED ? 2 : 1), PACKED>(acc, geo.i00, geo.pk0, geo.pk1, geo.pk2, geo.pk3, geo.cw, geo.W, vm, sm_lane);
       geo = next;
     };
@@ -417,6 +508,7 @@ __global__ void __launch_bounds__(kHpThreads, 1) msda_fwd_hp(const MsdaParams p)
 
     if (live) store_row<T, VEC>(out + ((size_t)b * p.Q * M + (size_t)(QPW * unit_quad(cur) + qi) * M + unit_head(cur)) * D + sub * VEC, acc);
     live = live_n;
+    st_c = st_n;
     cur = nxt;
     nxt = after;
     if constexpr (DYN) {

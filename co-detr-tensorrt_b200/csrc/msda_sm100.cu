@@ -2330,11 +2330,17 @@ int forward_impl(MsdaParams p, int dtype, unsigned flags, void *workspace, size_
     // bf16 without a math flag: FHFMA with each weight as two bf16 terms (msda_fwd_hp.cuh, kFhfmaSplit)
     const bool hp_split = dtype == MSDA_BF16 && plan.math == kExact && !(flags & MSDA_FLAG_MATH_EXACT) && env_int("MSDA_B200_BF16_SPLIT", 1);
     const bool hp_shape = (E == 2 || (E == 4 && env_int("MSDA_B200_HP_F32", 1))) && p.D == 32 && p.P == 4 && p.M == 8 && p.L >= 2 && p.L <= kHpMaxLevels &&
-                          NG <= sms && !fused && plan.split == 1 && plan.stage_bytes == 0 && !plan.dyn &&
-                          // exact-arithmetic calls (bf16 default, MSDA_FLAG_MATH_EXACT) stay on the vector kernel, which is
-                          // 3 % faster for them at the headline shape (58.9 vs 60.6 us); MSDA_B200_HP_EXACT=1 overrides
+                          NG <= sms && plan.split == 1 && plan.stage_bytes == 0 && !plan.dyn &&
+                          // fused producers stay on the vector kernel unless MSDA_B200_HP_FUSED=1: bit-identical here, but the softmax
+                          // and location arithmetic (+25 % instructions) cost this kernel more than that one -- 58.2 vs 54.1 us
+                          // (fp16), 72.3 vs 67.2 (bf16), 104.7 vs 99.3 (fp32) at the headline shape; reference points are
+                          // read as 32-bit words
+                          (!fused || ((p.ref_dim == 2 || p.ref_dim == 4) && aligned_to(p.ref, 4) && aligned_to(p.logits, E) && aligned_to(p.offsets, 2 * E) &&
+                                      env_int("MSDA_B200_HP_FUSED", 0))) &&
+                          // 16-bit calls with MSDA_FLAG_MATH_EXACT stay on the vector kernel (bf16: 57.3 us here vs 58.9 there,
+                          // fp16 slower here); MSDA_B200_HP_EXACT=1 overrides
                           (plan.math == kFhfma || E == 4 || hp_split || env_int("MSDA_B200_HP_EXACT", 0)) &&
-                          aligned_to(p.loc, 2 * E) && aligned_to(p.weight, E) && !(flags & MSDA_FLAG_NO_SMEM_LEVELS) &&
+                          (fused || (aligned_to(p.loc, 2 * E) && aligned_to(p.weight, E))) && !(flags & MSDA_FLAG_NO_SMEM_LEVELS) &&
                           // the kernel addresses an image's locations with 32-bit byte offsets
                           (int64_t)p.Q * p.M * p.L * 8 * E < ((int64_t)1 << 32);
     const int cpg = NG > 0 ? sms / NG : 0;
@@ -2349,6 +2355,7 @@ int forward_impl(MsdaParams p, int dtype, unsigned flags, void *workspace, size_
       hp_warps = env_int("MSDA_B200_HP_WARPS", hp_warps);
       if (hp_warps < 1) hp_warps = 1;
       if (hp_warps > kHpThreads / 32) hp_warps = kHpThreads / 32;
+      if (fused && hp_warps > kHpFusedThreads / 32) hp_warps = kHpFusedThreads / 32;
     }
     if (hp_shape && env_int("MSDA_B200_HP", 1) && quads >= hp_min_quads && !(workspace != nullptr && env_int("MSDA_B200_PACKED", 1))) {
       // Cached levels: the copy into shared memory costs every CTA ~1.5 us up front and takes L1 capacity away from
@@ -2373,7 +2380,7 @@ int forward_impl(MsdaParams p, int dtype, unsigned flags, void *workspace, size_
       // which is longer than the kernel.  Drawing chunks would cut the atomics but leave 1.2 chunks of 4 per warp, a
       // worse balance than the static one.  Only without cached levels and outside stream capture.
       bool hp_dyn = false;
-      if (p.hp_smem_bytes == 0 && env_int("MSDA_B200_HP_DYN", 0)) {
+      if (p.hp_smem_bytes == 0 && !fused && env_int("MSDA_B200_HP_DYN", 0)) {
         p.sched = sched_slots(p.B, stream);
         hp_dyn = p.sched != nullptr;
         // no rounds to fill evenly any more: as many warps as the register budget allows
@@ -2381,7 +2388,16 @@ int forward_impl(MsdaParams p, int dtype, unsigned flags, void *workspace, size_
         if (hp_warps < 1 || hp_warps > kHpThreads / 32) hp_warps = kHpThreads / 32;
       }
       int rch;
-      if (dtype == MSDA_F32) {
+      if (fused) {
+        if (dtype == MSDA_F32) rch = launch_hp(msda_fwd_hp<float, kExact, 8, false, false, true>);
+        else if (dtype == MSDA_F16)
+          rch = plan.math == kFhfma ? launch_hp(msda_fwd_hp<__half, kFhfma, 8, false, false, true>)
+                                    : launch_hp(msda_fwd_hp<__half, kExact, 8, false, false, true>);
+        else if (hp_split) rch = launch_hp(msda_fwd_hp<__nv_bfloat16, kFhfmaSplit, 8, false, false, true>);
+        else
+          rch = plan.math == kFhfma ? launch_hp(msda_fwd_hp<__nv_bfloat16, kFhfma, 8, false, false, true>)
+                                    : launch_hp(msda_fwd_hp<__nv_bfloat16, kExact, 8, false, false, true>);
+      } else if (dtype == MSDA_F32) {
         rch = hp_dyn ? launch_hp(msda_fwd_hp<float, kExact, 8, true>) : launch_hp(msda_fwd_hp<float, kExact, 8>);
       } else if (dtype == MSDA_F16) {
         if (hp_dyn) rch = plan.math == kFhfma ? launch_hp(msda_fwd_hp<__half, kFhfma, 8, true>) : launch_hp(msda_fwd_hp<__half, kExact, 8, true>);
@@ -2393,8 +2409,9 @@ int forward_impl(MsdaParams p, int dtype, unsigned flags, void *workspace, size_
         else rch = plan.math == kFhfma ? launch_hp(msda_fwd_hp<__nv_bfloat16, kFhfma, 8>) : launch_hp(msda_fwd_hp<__nv_bfloat16, kExact, 8>);
       }
       if (rch == 0)
-        snprintf(g_last_variant, sizeof(g_last_variant), "hp<%s,D32,P4,M%d>/smem%dK/%dwarps/%s%s", dtype_name(dtype), p.M,
-                 p.hp_smem_bytes / 1024, hp_warps, plan.math == kFhfma ? "fhfma" : (hp_split && !hp_dyn) ? "fhfma-split" : "exact", hp_dyn ? "/dyn" : "");
+        snprintf(g_last_variant, sizeof(g_last_variant), "hp<%s,D32,P4,M%d>/smem%dK/%dwarps/%s%s%s", dtype_name(dtype), p.M,
+                 p.hp_smem_bytes / 1024, hp_warps, plan.math == kFhfma ? "fhfma" : (hp_split && !hp_dyn) ? "fhfma-split" : "exact", hp_dyn ? "/dyn" : "",
+                 fused ? "/fused-producers" : "");
       return rch;
     }
   }

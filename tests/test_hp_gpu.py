@@ -224,3 +224,50 @@ def test_bf16_split_weight_fhfma_is_as_accurate_as_fp32_weights(cuda_device, mon
     monkeypatch.setenv("MSDA_B200_BF16_SPLIT", "0")
     _, _, v = errs(0)
     assert v.endswith("/exact"), v
+
+
+@pytest.mark.parametrize("dt", ["f16", "bf16", "f32"])
+@pytest.mark.parametrize("kind,q,smem_kb", [("encoder", 0, 0), ("encoder", 0, 148), ("decoder", 2501, 0), ("decoder", 2501, 36)])
+def test_head_pair_kernel_fused_producers(kind, q, smem_kb, dt, cuda_device, monkeypatch):
+    """msda_b200_forward_fused on the head-pair kernel: softmax over the pair's L*4 logits and the location arithmetic
+    (2-d reference points for the encoder, 4-d boxes for the decoder) in the geometry lanes.  Same helpers in the same
+    order as the vector kernel's fused mode -> bit-identical to it (bf16 default: split-weight FHFMA, compared within one
+    output rounding), and within the usual gate of the unfused pipeline built from the module's PyTorch ops."""
+    monkeypatch.setenv("MSDA_B200_SPLIT", "1")
+    monkeypatch.setenv("MSDA_B200_HP_MIN_QUADS_PER_WARP", "0")
+    monkeypatch.setenv("MSDA_B200_HP_SMEM", str(smem_kb * 1024))
+    monkeypatch.setenv("MSDA_B200_HP_FUSED", "1")                   # opt-in: measured slower than the vector kernel's fused mode
+    wl = W.Workload(name="hp_fused", shapes=tuple(W.pyramid_shapes(256, 384)), num_queries=q, batch=2, kind=kind, seed=17)
+    inp = W.make_inputs(wl)
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda_device)
+    cast = lambda a: dev(a).to(DT[dt])
+    ref_pts, off, lg = cast(inp.reference_points), cast(inp.sampling_offsets), cast(inp.attn_logits)
+    value, shapes, starts = cast(inp.value), dev(inp.spatial_shapes), dev(inp.level_start_index)
+    assert ref_pts.shape[-1] == (2 if kind == "encoder" else 4)
+    for fl in (0, cb.FLAG_MATH_EXACT) if dt != "f32" else (0,):
+        monkeypatch.setenv("MSDA_B200_HP_EXACT", "1")
+        want = cb.forward_fused(value, shapes, starts, ref_pts, off, lg, flags=fl | cb.FLAG_NO_SMEM_LEVELS)
+        torch.cuda.synchronize()
+        v0 = cb.last_variant()
+        assert v0.startswith("vec<") and v0.endswith("/fused-producers"), v0
+        before = cb.launch_count()
+        got = cb.forward_fused(value, shapes, starts, ref_pts, off, lg, flags=fl)
+        torch.cuda.synchronize()
+        v1 = cb.last_variant()
+        assert cb.launch_count() == before + 1
+        assert v1.startswith("hp<") and v1.endswith("/fused-producers") and f"smem{smem_kb}K" in v1, v1
+        if dt == "bf16" and fl == 0:
+            assert "/fhfma-split/" in v1, v1
+            assert max_rel(got.float().cpu().numpy(), want.float().cpu().numpy()) <= BF16_MAX_REL
+        else:
+            assert torch.equal(got, want), f"{v1} differs from {v0}: max abs {float((got.float() - want.float()).abs().max())}"
+    # against the unfused pipeline: the module's PyTorch ops in the tensor dtype, then the C oracle
+    from test_msda_gpu import _module_producers
+    loc, w = _module_producers(shapes, ref_pts, off, lg, wl.num_points)
+    ref = oracle.forward_c(value.float().cpu().numpy(), inp.spatial_shapes, inp.level_start_index,
+                           loc.float().cpu().numpy(), w.float().cpu().numpy())
+    g = got.float().cpu().numpy().astype(np.float64)
+    if dt == "f32":
+        assert float(np.linalg.norm(g - ref) / np.linalg.norm(ref)) <= 1e-5
+    else:
+        assert max_rel(g, ref) <= (HALF_MAX_REL if dt == "f16" else 2 * BF16_MAX_REL)
