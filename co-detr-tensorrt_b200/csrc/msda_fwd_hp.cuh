@@ -58,8 +58,9 @@ __device__ __forceinline__ uint4 lds128(unsigned addr) {
   return r;
 }
 
-// The four samples of one level for this lane group.  `rb` is the lane's row base: a 32-bit shared address
-// (SMEM: cached level, 128-byte pixel pitch) or a 64-bit global address (PIXB-byte pixel pitch).
+// The four samples of one level for this lane group.  Rows come from `sm_lane` (SMEM: the lane's 32-bit shared address
+// inside a cached level, 2 * D * sizeof(T) bytes per pixel) or from `vm` (64-bit global address of the lane's bytes of
+// its head in pixel 0, PIXB bytes per pixel).
 // PACKED: `vm` points into the pixel-pair packed pyramid (128-byte (pixel, head) entries that also hold the right-hand
 // neighbour, chunk-interleaved; PIXB = M * 128): the two corners of an image row arrive with ONE 32-byte load per lane
 // (LDG.E.256), one L1 wavefront per lane group instead of two.

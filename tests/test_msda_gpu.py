@@ -618,18 +618,50 @@ def test_dynamic_unit_scheduling_is_bit_identical(name, batch, dt, cuda_device, 
         assert torch.equal(captured, want)
 
 
-def test_degenerate_shapes_give_zeros(cuda_device):
-    """No levels or no points: the sum is empty, the output is all zeros (and still fully written)."""
+@pytest.mark.parametrize("queries", [5, 20000])
+def test_degenerate_shapes_give_zeros(queries, cuda_device):
+    """No levels or no points: the sum is empty, the output is all zeros (and still fully written) -- also at a query
+    count that would otherwise take the persistent fast kernels, whose input pre-loads must not run on empty tensors."""
     v = torch.randn(2, 10, 8, 32, device=cuda_device, dtype=torch.float16)
     for levels, points in ((0, 4), (2, 0)):
         shapes = torch.tensor([[2, 3], [2, 2]][:levels], dtype=torch.int64, device=cuda_device).reshape(levels, 2)
         lsi = torch.tensor([0, 6][:levels], dtype=torch.int64, device=cuda_device)
-        loc = torch.rand(2, 5, 8, levels, points, 2, device=cuda_device, dtype=torch.float16)
-        w = torch.rand(2, 5, 8, levels, points, device=cuda_device, dtype=torch.float16)
-        out = torch.full((2, 5, 256), float("nan"), device=cuda_device, dtype=torch.float16)
+        loc = torch.rand(2, queries, 8, levels, points, 2, device=cuda_device, dtype=torch.float16)
+        w = torch.rand(2, queries, 8, levels, points, device=cuda_device, dtype=torch.float16)
+        out = torch.full((2, queries, 256), float("nan"), device=cuda_device, dtype=torch.float16)
         cb.forward_into(v, shapes, lsi, loc, w, out)
         torch.cuda.synchronize()
+        assert cb.last_variant().startswith("generic<")
         assert torch.count_nonzero(out) == 0 and not torch.isnan(out).any()
+
+
+@pytest.mark.parametrize("dt", ["f16", "bf16", "f32"])
+@pytest.mark.parametrize("shape", ["small", "head_pair_sized"])
+def test_locations_at_an_odd_element_offset(shape, dt, cuda_device):
+    """A contiguous `sampling_loc` that is a view one element into a larger buffer is aligned for its elements but not
+    for the (x, y) pair loads of the fast kernels: it must take the element-wise kernel and give the same result as
+    an aligned copy -- not a misaligned-address fault, which would poison the CUDA context for the whole process."""
+    shapes = W.pyramid_shapes(64, 96) if shape == "small" else W.pyramid_shapes(384, 256)
+    wl = W.Workload(name="odd", shapes=tuple(shapes), num_queries=0, batch=1, kind="encoder", seed=23)
+    inp = W.make_inputs(wl, out_of_range_frac=0.05)
+    d = to_dev({k: getattr(inp, k) for k in ARRAY_KEYS}, TORCH_DT[dt], cuda_device)
+    want = cb.multi_scale_deformable_attention(*(d[k] for k in ARRAY_KEYS), flags=cb.FLAG_MATH_EXACT)
+    assert not cb.last_variant().startswith("generic<")
+    loc = d["sampling_loc"]
+    buf = torch.empty(loc.numel() + 1, dtype=loc.dtype, device=cuda_device)
+    view = buf[1:].view(loc.shape)
+    view.copy_(loc)
+    assert view.is_contiguous() and view.data_ptr() % (2 * loc.element_size()) != 0
+    got = cb.multi_scale_deformable_attention(d["value"], d["spatial_shapes"], d["level_start_index"], view, d["attn_weight"],
+                                              flags=cb.FLAG_MATH_EXACT)
+    torch.cuda.synchronize()
+    assert cb.last_variant().startswith("generic<"), cb.last_variant()
+    ref = ref32_of(d)
+    if dt == "f32":
+        assert rel_l2(got.cpu().numpy(), ref) <= FP32_REL_L2
+    else:
+        assert max_rel(got.float().cpu().numpy(), ref) <= (HALF_MAX_REL if dt == "f16" else BF16_MAX_REL)
+        assert max_rel(got.float().cpu().numpy(), want.float().cpu().numpy()) <= (HALF_MAX_REL if dt == "f16" else BF16_MAX_REL)
 
 
 def test_concurrent_streams_and_threads(cuda_device):
