@@ -748,3 +748,48 @@ print("PYTHON_OP_OK")
     env = dict(os.environ, MSDA_B200_PYTHON_OP="1")
     out = subprocess.run([sys.executable, "-c", f"ROOT = {os.path.dirname(GOLDEN)[:-6]!r}\n" + code], capture_output=True, text=True, env=env, timeout=600)
     assert out.returncode == 0 and "PYTHON_OP_OK" in out.stdout, out.stdout + out.stderr
+
+
+# ----------------------------------------------------------------------------------------------
+# seeded random shapes across every dispatch boundary
+# ----------------------------------------------------------------------------------------------
+def _random_problem(seed):
+    """Heads, channels, levels, points, level sizes, query count and batch drawn from a seed: shapes the fixed fixtures do
+    not name (odd channel counts, a single level, 1-pixel levels, 8 points, 16 heads, query counts around the kernels'
+    group sizes) so that every kernel family and every fallback edge sees inputs it was not tuned for."""
+    rng = np.random.default_rng(1000 + seed)
+    M = int(rng.choice([1, 2, 3, 4, 8, 16]))
+    D = int(rng.choice([8, 16, 24, 32, 32, 32, 64]))
+    L = int(rng.integers(1, 7))
+    P = int(rng.choice([1, 2, 4, 4, 4, 8]))
+    shapes = [(int(rng.integers(1, 40)), int(rng.integers(1, 40))) for _ in range(L)]
+    S = sum(h * w for h, w in shapes)
+    Q = int(rng.choice([1, 3, 4, 5, 31, 32, 33, 127, 900, 2500, 7001]))
+    B = int(rng.integers(1, 4))
+    starts = np.cumsum([0] + [h * w for h, w in shapes[:-1]]).astype(np.int64)
+    value = rng.standard_normal((B, S, M, D)).astype(np.float32)
+    loc = rng.uniform(-0.15, 1.15, size=(B, Q, M, L, P, 2)).astype(np.float32)
+    edge = rng.random(loc.shape) < 0.03        # exactly on the borders of the range test (ms_deform_attn.cu:249)
+    loc[edge] = rng.choice(np.array([0.0, 1.0], dtype=np.float32), size=int(edge.sum()))
+    w = rng.random((B, Q, M, L, P)).astype(np.float32)
+    w /= w.sum(axis=(-1, -2), keepdims=True)
+    return {"value": value, "spatial_shapes": np.asarray(shapes, dtype=np.int64), "level_start_index": starts,
+            "sampling_loc": loc, "attn_weight": w}
+
+
+@pytest.mark.parametrize("dt", ["f32", "f16", "bf16"])
+@pytest.mark.parametrize("seed", range(24))
+def test_random_shapes_against_oracle(seed, dt, cuda_device):
+    arrs = _random_problem(seed)
+    for flags in (0, cb.FLAG_FORCE_GENERIC):
+        before = cb.launch_count()
+        out, d = run_op(arrs, TORCH_DT[dt], cuda_device, flags)
+        assert cb.launch_count() > before
+        ref = ref32_of(d)
+        got = out.float().cpu().numpy()
+        B, Q = arrs["sampling_loc"].shape[:2]
+        assert got.shape == (B, Q, arrs["value"].shape[2] * arrs["value"].shape[3])
+        if dt == "f32":
+            assert rel_l2(got, ref) <= FP32_REL_L2, cb.last_variant()
+        else:
+            assert max_rel(got, ref) <= (HALF_MAX_REL if dt == "f16" else BF16_MAX_REL), cb.last_variant()
