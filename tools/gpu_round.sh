@@ -7,6 +7,7 @@
 #   ncu        launch list of the bench command + `--set full` capture of the headline kernel (+ profiles/traffic.json)
 #   ncudec     `--set full` capture of the decoder call       ncuvec   same for the all-global vector kernel (MSDA_B200_HP=0)
 #   ncudtypes  `--set full` captures of the headline shape in bf16 and fp32      hpdtypes   their A/B timings + bf16 accuracy
+#   ncuall     `--set full` captures of configs[1] and configs[4] (feeds profiles/traffic.json)
 #   hp         head-pair kernel A/B against the vector kernel on every workload (tests/perf_hp.py)
 #   hpsweep    warps-per-CTA / shared-memory sweep of the head-pair kernel + every tuning build under build_variants/
 #   sweep      tests/perf_sweep.py (all configurations, reference CUDA kernel beside ours)
@@ -46,6 +47,9 @@ for st in $STAGES; do
     ncudec)
       NCU_ARGS="swinl_dec_1152x768 float16 1" ncu_full decoder
       python tools/update_traffic.py gpurun_out/prof_decoder.ncu-rep swinl_dec_1152x768/float16/b1 0 "profiles/r02_ncu_decoder_summary.txt (gpurun_out/prof_decoder.ncu-rep)" ;;
+    ncuall)  # the remaining encoder configurations (captures for profiles/traffic.json; two reports stay under gpurun's 64 MiB)
+      NCU_ARGS="r50_enc_608 float16 1" ncu_full r50
+      NCU_ARGS="swinl_enc_1920x1280 float16 2" ncu_full enc1920 ;;
     ncuvec)
       NCU_ARGS="swinl_enc_1152x768 float16 1" ncu_full vec MSDA_B200_HP=0 ;;
     ncudtypes)
