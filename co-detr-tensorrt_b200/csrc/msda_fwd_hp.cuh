@@ -235,6 +235,8 @@ __global__ void __launch_bounds__(FUSED ? kHpFusedThreads : kHpThreads, 1) msda_
 
   pdl_launch_dependents();
   pdl_wait_prior_grid();
+  // cold call: the CTAs of an image ask L2 for its whole pyramid up front (one bulk prefetch each, see prefetch_value_l2)
+  if constexpr (!PACKED) prefetch_value_l2(p, E);
 
   constexpr int M = MT;
   const int NG = M >> 1;                      // head pairs
